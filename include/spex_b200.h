@@ -1,0 +1,245 @@
+/*
+ * spex_b200.h — C-ABI of libspex_b200.so, the sm_100a hot path behind SPEX's LightGCN_SPEX.
+ *
+ * The reference (XMUDM/SPEX) is pure Python: it has no FFI of its own.  Every entry point below
+ * therefore replaces a *PyTorch library call site* of the reference; the site is cited per
+ * function as <file>:<line> relative to /root/reference/.  The binding a maintainer of the
+ * reference would add is a ctypes stub — no torch types cross this boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; 0 = ok, >0 = cudaError_t, <0 = SPEX_E_* argument error;
+ *   - the library never allocates device memory that outlives a call; workspaces are passed in;
+ *   - embedding tables are row-major fp32 [rows, D], rows 16-byte aligned (D % 4 == 0);
+ *   - CSR adjacency: rowptr int64 [n_rows+1], col int32 [nnz] ascending per row, val fp32 [nnz];
+ *   - results are deterministic: no floating-point atomics anywhere (north_star (1),(2)).
+ */
+#ifndef SPEX_B200_H
+#define SPEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPEX_ABI_VERSION 1
+
+/* argument errors (negative; positive values are cudaError_t) */
+#define SPEX_E_BADARG   (-1)  /* null pointer / negative size */
+#define SPEX_E_BADDIM   (-2)  /* D unsupported (must be a multiple of 4, <= 512) */
+#define SPEX_E_ALIGN    (-3)  /* pointer not 16-byte aligned */
+#define SPEX_E_ARCH     (-4)  /* device is not sm_100 (no fallback path exists) */
+#define SPEX_E_TOOBIG   (-5)  /* k / batch exceeds a compiled-in limit */
+#define SPEX_E_WORKSPACE (-6) /* workspace too small */
+
+int spex_abi_version(void);
+/* human-readable name of a code returned by any function below (static storage). */
+const char* spex_error_string(int code);
+/* fills sm_count / compute capability of the current device; SPEX_E_ARCH if cc != 10.x */
+int spex_device_check(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t spex_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Long-row plan.  Rows with more than `seg_len` non-zeros are cut into segments of seg_len
+ * edges; each segment is reduced by one warp into a partial row and the partials of a row are
+ * summed in segment order (deterministic two-pass — no atomics).  The plan is built once per
+ * graph by the host (spex_b200/graph.py: plan_long_rows) and passed to every SpMM as a HOST
+ * struct holding device pointers; NULL (or n_long == 0) means "no long rows".
+ * ------------------------------------------------------------------------------------------ */
+typedef struct spex_long_plan {
+  int32_t seg_len;            /* segment length in edges (>= 32)                              */
+  int32_t n_long;             /* number of rows with degree > seg_len                         */
+  int32_t n_seg;              /* total number of segments = long_segptr[n_long]               */
+  int32_t reserved;
+  const int32_t* long_rows;   /* int32 [n_long]    row ids, ascending                         */
+  const int32_t* long_segptr; /* int32 [n_long+1]  exclusive scan of ceil(deg/seg_len)        */
+  float* partial;             /* fp32  [n_seg, D]  workspace                                  */
+} spex_long_plan;
+
+/*
+ * One propagation layer  Y = A·X  with a fused two-output epilogue
+ *      Y[i,:] = acc                                   (skipped if Y == NULL)
+ *      Z[i,:] = (addend[i,:] * addend_scale + acc) * z_scale   (skipped if Z == NULL;
+ *                                                      addend == NULL means 0)
+ * Replaces torch.sparse.mm(g_droped, all_emb)  LightGCN_SPEX/code/utility1/model.py:91
+ * (same call: model_expert_s.py:120) and, through Z, the stack+mean of model.py:94-95 and the
+ * autograd of both (main_rec.py:35).  The CSR may be a row block of the full matrix (row partition across GPUs,
+ * SURVEY §8e): X is always the full [n_cols, D] table, Y/Z/addend are [n_rows, D] (local rows).
+ */
+int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                      const float* X, int64_t n_rows, int32_t D,
+                      float* Y, const float* addend, float addend_scale,
+                      float* Z, float z_scale,
+                      const spex_long_plan* plan, void* stream);
+
+/*
+ * K-layer propagation + layer mean:  out = (E0 + A·E0 + ... + A^K·E0) / (K+1)
+ * E0 [N,D] is the concatenated user+item table (model.py:72); tmp0/tmp1 are [N,D] ping-pong
+ * workspaces (K>=2 needs tmp0, K>=3 needs both).  The mean is accumulated in `out` by every
+ * layer's epilogue; the last layer never writes its E^(K) to memory.
+ * Replaces LightGCN.computer()  model.py:66-97 (K1+K2+K3 of SURVEY §2.1).
+ */
+int spex_propagate_mean_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                            const float* E0, int64_t N, int32_t D, int32_t K,
+                            float* out, float* tmp0, float* tmp1,
+                            const spex_long_plan* plan, void* stream);
+
+/*
+ * Backward of spex_propagate_mean_f32 w.r.t. E0, given g = dL/d(out):
+ *      G_K = g/(K+1);  G_k = g/(K+1) + A^T·G_{k+1};  dE0 = G_0
+ * (rowptr,col,val) must describe A^T (for the symmetric normalised adjacency it is A itself;
+ * with edge dropout pass the transposed values, see spex_gather_f32).
+ * Replaces autograd through model.py:83-95 (K6 of SURVEY §2.1).
+ */
+int spex_propagate_mean_bwd_f32(const int64_t* rowptr, const int32_t* col, const float* valT,
+                                const float* g, int64_t N, int32_t D, int32_t K,
+                                float* dE0, float* tmp0, float* tmp1,
+                                const spex_long_plan* plan, void* stream);
+
+/* out[i] = src[idx[i]] * scale[i]  (scale may be NULL).  Used for the dropout graph
+ * (model.py:46-55: kept values / keep_prob as a per-nnz multiplier) and for A^T values. */
+int spex_gather_f32(const float* src, const int64_t* idx, const float* scale, float* out,
+                    int64_t n, void* stream);
+
+/*
+ * BCE step (reference loss): gamma[b] = <U[users[b]], I[items[b]]>  (model.py:115-118),
+ * loss = mean BCEWithLogits(gamma, labels) (model.py:23,120).
+ *   U, I      propagated user / item tables (views of `out` above), row stride D
+ *   gamma     fp32 [B]   (always written; flag=1 of forward() returns it)
+ *   loss      fp32 [1]   (NULL to skip: then labels may be NULL too)
+ *   dgamma    fp32 [B]   dloss/dgamma = (sigmoid(gamma)-label)/B   (NULL to skip)
+ */
+int spex_bce_fwd_f32(const float* U, const float* I, int32_t D,
+                     const int64_t* users, const int64_t* items, const float* labels,
+                     int64_t B, float* gamma, float* loss, float* dgamma, void* stream);
+
+/*
+ * Backward of the gather-dot: scatter dgamma[b]*I[items[b]] into gU[users[b]] and
+ * dgamma[b]*U[users[b]] into gI[items[b]], times upstream scalar *grad_loss (device fp32[1],
+ * NULL = 1).  Duplicate indices are reduced in batch order by a segmented scan — no atomics
+ * (replaces index_put_(accumulate=True), K6).  gU/gI must be zero-filled by the caller for rows
+ * not touched; touched rows are overwritten.
+ */
+int spex_bce_bwd_f32(const float* U, const float* I, int32_t D,
+                     const int64_t* users, const int64_t* items, const float* dgamma,
+                     const float* grad_loss, int64_t B, float* gU, float* gI, void* stream);
+
+/*
+ * BPR step (north_star addition; semantics of upstream LightGCN bpr_loss):
+ *   loss = mean softplus(<u,n> - <u,p>),  reg = 0.5*(|U0[u]|^2+|I0[p]|^2+|I0[n]|^2)/B
+ *   out2 fp32 [2] = {loss, reg};  dscore fp32 [B] = sigmoid(<u,n>-<u,p>)/B  (NULL to skip)
+ *   work2B fp32 [2*B] workspace (per-sample terms, reduced in a fixed order)
+ */
+int spex_bpr_fwd_f32(const float* U, const float* I, const float* U0, const float* I0, int32_t D,
+                     const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t B,
+                     float* out2, float* dscore, float* work2B, void* stream);
+
+/*
+ * BPR backward.  grad2 (device fp32[2]) = upstream {dL/dloss, dL/dreg}.
+ *   gU[u] += gl*dscore*(n-p); gI[p] += -gl*dscore*u; gI[n] += gl*dscore*u   (propagated tables)
+ *   gU0[u] += gr*U0[u]/B; gI0[p] += gr*I0[p]/B; gI0[n] += gr*I0[n]/B        (ego tables)
+ * Same deterministic segmented reduction as spex_bce_bwd_f32; touched rows are overwritten,
+ * untouched rows must have been zero-filled by the caller.
+ */
+int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const float* I0, int32_t D,
+                     const int64_t* users, const int64_t* pos, const int64_t* neg,
+                     const float* dscore, const float* grad2, int64_t B,
+                     float* gU, float* gI, float* gU0, float* gI0, void* stream);
+
+/*
+ * Dense Adam over one table (torch.optim.Adam semantics, main_rec.py:23,37; K7):
+ *   m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g;
+ *   p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ */
+int spex_adam_f32(float* p, const float* g, float* m, float* v, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/*
+ * Expert gating epilogue (configs[1], model_expert_s.py:154-161):
+ *   att = softmax([E0 | Eout] · W[2D,2]);  out = E0*att0 + Eout*att1     per row
+ */
+int spex_expert_gate_f32(const float* E0, const float* Eout, const float* W, int64_t n,
+                         int32_t D, float* out, void* stream);
+
+/*
+ * Full-ranking top-k, exact fp32 SIMT path:  for each of B users, the k best items of
+ * <U[users[b]], I[j]>, j in [0, m_items), excluding the user's training items
+ * (mask_rowptr int64 [n_mask_rows+1], mask_col int32 ascending per row: CSR of R; NULL = none).
+ * Ordering: score descending, ties by ascending item id.  Slots beyond the number of
+ * unmasked items get idx = -1, val = -inf.
+ *   out_idx int32 [B,k], out_val fp32 [B,k];  k <= 128
+ * Replaces getUsersRating (abstract at model.py:14-15) + torch.topk; this is the bit-exact
+ * companion of the tensor-core path below.
+ */
+int spex_score_topk_f32(const float* U, const float* I, int32_t D,
+                        const int64_t* users, int64_t B, int64_t m_items,
+                        const int64_t* mask_rowptr, const int32_t* mask_col,
+                        int32_t k, int32_t* out_idx, float* out_val, void* stream);
+
+/*
+ * fp32 [rows, D] -> bf16 (round-to-nearest-even) in the UMMA K-major "no-swizzle" canonical
+ * layout: byte offset of element (r, k) = (r/8)*(16*D) + (k/8)*128 + (r%8)*16 + (k%8)*2, i.e.
+ * 8-row x 16-byte core matrices, one 8-row group contiguous.  Optional row gather
+ * (rows == NULL: identity); rows [n, n_pad) are zero; n_pad % 8 == 0, D % 8 == 0.
+ * dst holds n_pad*D bf16.  Feeds spex_score_topk_bf16.
+ */
+int spex_pack_bf16(const float* src, const int64_t* rows, int64_t n, int64_t n_pad, int32_t D,
+                   void* dst_bf16, void* stream);
+
+/*
+ * Full-ranking top-k on the 5th-gen tensor cores (tcgen05.mma kind::f16, bf16 in / fp32 TMEM
+ * accumulators), D == 64.  Ub [B_pad,64] / Ib [m_pad,64] are packed tables from spex_pack_bf16
+ * (B_pad % 128 == 0, m_pad % 256 == 0).  Scores never reach HBM: the epilogue streams TMEM,
+ * rejects below the per-row running k-th score, applies the training-item mask to survivors
+ * and keeps a per-row top-k.  `user_ids` int64 [B] gives the mask row of each scored row
+ * (NULL: row b uses mask row b).  Same ordering / output contract as spex_score_topk_f32;
+ * k <= 64.  No workspace.
+ */
+int spex_score_topk_bf16(const void* Ub, const void* Ib, int64_t B, int64_t B_pad,
+                         int64_t m_items, int64_t m_pad, const int64_t* user_ids,
+                         const int64_t* mask_rowptr, const int32_t* mask_col,
+                         int32_t k, int32_t* out_idx, float* out_val, void* stream);
+
+/*
+ * Sampled-candidate scoring for the reference Test() (batch_test.py:28-40, hoisted):
+ *   score[u,c] = <U[users[u]], I[cand[u,c]]>,  cand int32 [n_u, n_c]  ->  score fp32 [n_u, n_c]
+ */
+int spex_score_candidates_f32(const float* U, const float* I, int32_t D,
+                              const int64_t* users, const int32_t* cand, int64_t n_u,
+                              int32_t n_c, float* score, void* stream);
+
+/*
+ * NGCF layer epilogue (configs[2], NGCF_SPEX/code/main_rec.py:76-85), D == 64:
+ *   out = lrelu(side·W1^T + b1) + lrelu((ego*side)·W2^T + b2);  norm = out / max(|out|_2, 1e-12)
+ * side = A·ego comes from spex_spmm_csr_f32.  W row-major [64,64] (nn.Linear.weight layout).
+ * `out` is the next layer's ego (pre-normalisation, dropout applied by the caller in training),
+ * `norm` is written with row stride norm_stride floats (the concat buffer of main_rec.py:85).
+ */
+int spex_ngcf_epilogue_f32(const float* ego, const float* side, const float* W1, const float* b1,
+                           const float* W2, const float* b2, int64_t n, int32_t D,
+                           float negative_slope, float* out, float* norm, int64_t norm_stride,
+                           void* stream);
+
+/*
+ * CUDA-IPC helpers for the row-partitioned multi-GPU path: each rank allocates its
+ * exchange buffer with spex_ipc_alloc, publishes the 64-byte handle, and opens its peers'.
+ * spex_spmm_csr_f32_push is spex_spmm_csr_f32 whose Y epilogue also stores every output row
+ * into up to 8 peer tables (P2P stores over NVLink): SpMM and all-gather in one kernel.
+ */
+int spex_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64_host);
+int spex_ipc_open(const void* handle64_host, void** dev_ptr);
+int spex_ipc_close(void* dev_ptr);
+int spex_ipc_free(void* dev_ptr);
+int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,
+                           const float* X, int64_t n_rows, int32_t D,
+                           int64_t out_row_offset, float* const* peer_Y_host, int32_t n_peers,
+                           const float* addend, float addend_scale, float* Z, float z_scale,
+                           const spex_long_plan* plan, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEX_B200_H */

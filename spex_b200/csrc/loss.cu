@@ -1,0 +1,485 @@
+// loss.cu — fused gather -> dot -> loss kernels and their deterministic backward (sm_100a).
+//
+// Replaces, in the reference:
+//   all_users[users], all_items[items], mul, sum      LightGCN_SPEX/code/utility1/model.py:115-118
+//   nn.BCEWithLogitsLoss                              model.py:23,120
+//   index backward = index_put_(accumulate=True)      autograd, main_rec.py:35   (atomics there)
+//   torch.optim.Adam.step                             main_rec.py:23,37
+//   expert gating                                     model_expert_s.py:154-161
+//   per-user candidate scoring of Test()              utility1/batch_test.py:28-40
+// and adds bpr_loss (north_star; upstream LightGCN semantics).
+//
+// All kernels are HBM/L2-latency bound gathers of 256-byte rows: warp per sample, 128-bit lanes.
+// The backward scatter is a segmented reduction in batch order (first occurrence of a row id owns
+// the output row and sums every duplicate in ascending batch position): no atomics, so gradients
+// are bit-reproducible.
+#include "common.cuh"
+#include <math.h>
+
+namespace spex {
+
+constexpr int kWarpsPerCta = 8;
+
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, int64_t row, int D, int lane,
+                                         float4 (&r)[NV]) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    r[v] = (d < D) ? *reinterpret_cast<const float4*>(base + row * D + d) : f4_zero();
+  }
+}
+template <int NV>
+__device__ __forceinline__ float dot_rows(const float4 (&a)[NV], const float4 (&b)[NV]) {
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    s = fmaf(a[v].x, b[v].x, s);
+    s = fmaf(a[v].y, b[v].y, s);
+    s = fmaf(a[v].z, b[v].z, s);
+    s = fmaf(a[v].w, b[v].w, s);
+  }
+  return s;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// softplus(x) = max(x,0) + log1p(exp(-|x|))
+__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+bce_fwd_kernel(const float* __restrict__ U, const float* __restrict__ I, int D,
+               const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+               const float* __restrict__ labels, int64_t B, float* __restrict__ gamma,
+               float* __restrict__ dgamma) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float4 u[NV], it[NV];
+  load_row<NV>(U, users[b], D, lane, u);
+  load_row<NV>(I, items[b], D, lane, it);
+  const float g = warp_sum(dot_rows<NV>(u, it));
+  if (lane == 0) {
+    gamma[b] = g;
+    if (dgamma) dgamma[b] = (sigmoidf_(g) - labels[b]) / (float)B;
+  }
+}
+
+// single CTA, fixed-order tree: loss = mean_b [(1-y)x + max(-x,0) + log1p(exp(-|x|))]
+__global__ void __launch_bounds__(1024)
+bce_loss_reduce_kernel(const float* __restrict__ gamma, const float* __restrict__ labels, int64_t B,
+                       float* __restrict__ loss) {
+  __shared__ float sh[1024];
+  float s = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += 1024) {
+    const float x = gamma[b], y = labels[b];
+    s += (1.f - y) * x + fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = sh[0] / (float)B;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic scatter:  out[idx(t), :] = sum over t' with idx(t') == idx(t), ascending t', of
+//                         w(t') * src[srcidx(t'), :]
+// The logical list has nseg*B entries; entry t = (seg = t / B, b = t % B).
+struct ScatterList {
+  const int64_t* idx[2];
+  const int64_t* src_idx[2];
+  float sign[2];
+  int nseg;
+  int64_t B;
+  const float* coef;     // per-sample [B] or NULL (=1)
+  const float* gscalar;  // device scalar or NULL (=1)
+  float cconst;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+scatter_rows_kernel(ScatterList L, const float* __restrict__ src, float* __restrict__ out, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)L.nseg * L.B;
+  const int64_t t = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (t >= total) return;
+  const int myseg = (int)(t / L.B);
+  const int64_t my = L.idx[myseg][t - (int64_t)myseg * L.B];
+  const float gs = (L.gscalar ? L.gscalar[0] : 1.f) * L.cconst;
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = f4_zero();
+  for (int64_t base = 0; base < total; base += 32) {
+    const int64_t tt = base + lane;
+    bool match = false;
+    if (tt < total) {
+      const int sg = (int)(tt / L.B);
+      match = (L.idx[sg][tt - (int64_t)sg * L.B] == my);
+    }
+    unsigned m = __ballot_sync(kFull, match);
+    if (base + 32 <= t) {
+      if (m) return;  // an earlier entry owns this row
+    } else if (base <= t) {
+      const unsigned before = (1u << (int)(t - base)) - 1u;
+      if (m & before) return;
+    }
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t t2 = base + bit;
+      const int sg = (int)(t2 / L.B);
+      const int64_t b2 = t2 - (int64_t)sg * L.B;
+      const float w = L.sign[sg] * (L.coef ? L.coef[b2] : 1.f) * gs;
+      float4 r[NV];
+      load_row<NV>(src, L.src_idx[sg][b2], D, lane, r);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f4_fma(acc[v], w, r[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    if (d < D) *reinterpret_cast<float4*>(out + my * D + d) = acc[v];
+  }
+}
+
+static int launch_scatter(const ScatterList& L, const float* src, float* out, int D, cudaStream_t st) {
+  const int64_t total = (int64_t)L.nseg * L.B;
+  if (total == 0) return 0;
+  if (total > (1 << 18)) return SPEX_E_TOOBIG;  // O(total^2/32) duplicate scan; see DESIGN.md
+  const unsigned grid = (unsigned)((total + kWarpsPerCta - 1) / kWarpsPerCta);
+  if (D <= 128)
+    scatter_rows_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(L, src, out, D);
+  else
+    scatter_rows_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(L, src, out, D);
+  count_launch();
+  return check_last();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+bpr_fwd_kernel(const float* __restrict__ U, const float* __restrict__ I, const float* __restrict__ U0,
+               const float* __restrict__ I0, int D, const int64_t* __restrict__ users,
+               const int64_t* __restrict__ pos, const int64_t* __restrict__ neg, int64_t B,
+               float* __restrict__ dscore, float* __restrict__ work) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int64_t u = users[b], p = pos[b], n = neg[b];
+  float4 ru[NV], rp[NV], rn[NV];
+  load_row<NV>(U, u, D, lane, ru);
+  load_row<NV>(I, p, D, lane, rp);
+  load_row<NV>(I, n, D, lane, rn);
+  const float ps = warp_sum(dot_rows<NV>(ru, rp));
+  const float ns = warp_sum(dot_rows<NV>(ru, rn));
+  load_row<NV>(U0, u, D, lane, ru);
+  load_row<NV>(I0, p, D, lane, rp);
+  load_row<NV>(I0, n, D, lane, rn);
+  const float rg = warp_sum(dot_rows<NV>(ru, ru) + dot_rows<NV>(rp, rp) + dot_rows<NV>(rn, rn));
+  if (lane == 0) {
+    const float x = ns - ps;
+    work[b] = softplusf_(x);
+    work[B + b] = 0.5f * rg;
+    if (dscore) dscore[b] = sigmoidf_(x) / (float)B;
+  }
+}
+
+// out2 = { mean(work[0:B]), sum(work[B:2B]) / B }, fixed-order tree
+__global__ void __launch_bounds__(1024)
+pair_mean_reduce_kernel(const float* __restrict__ work, int64_t B, float* __restrict__ out2) {
+  __shared__ float sh0[1024];
+  __shared__ float sh1[1024];
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t b = threadIdx.x; b < B; b += 1024) {
+    s0 += work[b];
+    s1 += work[B + b];
+  }
+  sh0[threadIdx.x] = s0;
+  sh1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh0[threadIdx.x] += sh0[threadIdx.x + o];
+      sh1[threadIdx.x] += sh1[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out2[0] = sh0[0] / (float)B;
+    out2[1] = sh1[0] / (float)B;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+            float4* __restrict__ v, int64_t n4, float beta1, float beta2, float eps, float step_size,
+            float bc2_sqrt, float* __restrict__ ptail, const float* __restrict__ gtail,
+            float* __restrict__ mtail, float* __restrict__ vtail, int ntail) {
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    mm = mm + (gg - mm) * omb1;                 // exp_avg.lerp_(grad, 1-beta1)
+    vv = vv * beta2 + omb2 * gg * gg;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp = pp - step_size * (mm / denom);         // param.addcdiv_(exp_avg, denom, -step_size)
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = __ldcs(g + i);
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    p[i] = pp;
+    m[i] = mm;
+    v[i] = vv;
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) {
+    const int t = threadIdx.x;
+    upd(ptail[t], gtail[t], mtail[t], vtail[t]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expert gating (model_expert_s.py:154-161): warp per row
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+expert_gate_kernel(const float* __restrict__ E0, const float* __restrict__ Eout,
+                   const float* __restrict__ W, int64_t n, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float4 a[NV], b[NV];
+  load_row<NV>(E0, row, D, lane, a);
+  load_row<NV>(Eout, row, D, lane, b);
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    if (d < D) {
+      const float av[4] = {a[v].x, a[v].y, a[v].z, a[v].w};
+      const float bv[4] = {b[v].x, b[v].y, b[v].z, b[v].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 wa = *reinterpret_cast<const float2*>(W + 2 * (d + q));
+        const float2 wb = *reinterpret_cast<const float2*>(W + 2 * (D + d + q));
+        l0 = fmaf(av[q], wa.x, l0);
+        l1 = fmaf(av[q], wa.y, l1);
+        l0 = fmaf(bv[q], wb.x, l0);
+        l1 = fmaf(bv[q], wb.y, l1);
+      }
+    }
+  }
+  l0 = warp_sum(l0);
+  l1 = warp_sum(l1);
+  const float mx = fmaxf(l0, l1);
+  const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+  const float a0 = e0 / (e0 + e1), a1 = e1 / (e0 + e1);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    if (d < D) {
+      float4 o;
+      o.x = a[v].x * a0 + b[v].x * a1;
+      o.y = a[v].y * a0 + b[v].y * a1;
+      o.z = a[v].z * a0 + b[v].z * a1;
+      o.w = a[v].w * a0 + b[v].w * a1;
+      *reinterpret_cast<float4*>(out + row * D + d) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// score[u,c] = <U[users[u]], I[cand[u,c]]>: warp per (u,c)
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+score_candidates_kernel(const float* __restrict__ U, const float* __restrict__ I, int D,
+                        const int64_t* __restrict__ users, const int32_t* __restrict__ cand,
+                        int64_t n_u, int n_c, float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (w >= n_u * n_c) return;
+  const int64_t u = w / n_c;
+  float4 a[NV], b[NV];
+  load_row<NV>(U, users[u], D, lane, a);
+  load_row<NV>(I, (int64_t)cand[w], D, lane, b);
+  const float s = warp_sum(dot_rows<NV>(a, b));
+  if (lane == 0) score[w] = s;
+}
+
+static inline unsigned warp_grid(int64_t n) { return (unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta); }
+
+}  // namespace spex
+
+using namespace spex;
+
+#define SPEX_CHECK_TABLE(D)                                        \
+  SPEX_RETURN_IF((D) <= 0 || ((D)&3) || (D) > 512, SPEX_E_BADDIM)
+
+extern "C" int spex_bce_fwd_f32(const float* U, const float* I, int32_t D, const int64_t* users,
+                                const int64_t* items, const float* labels, int64_t B, float* gamma,
+                                float* loss, float* dgamma, void* stream) {
+  SPEX_RETURN_IF(!U || !I || !users || !items || !gamma || B < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF((loss || dgamma) && !labels, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I), SPEX_E_ALIGN);
+  SPEX_RETURN_IF(B > 0x7fffffffLL, SPEX_E_TOOBIG);
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D <= 128)
+    bce_fwd_kernel<1><<<warp_grid(B), kWarpsPerCta * 32, 0, st>>>(U, I, D, users, items, labels, B, gamma, dgamma);
+  else
+    bce_fwd_kernel<4><<<warp_grid(B), kWarpsPerCta * 32, 0, st>>>(U, I, D, users, items, labels, B, gamma, dgamma);
+  count_launch();
+  if (loss) {
+    bce_loss_reduce_kernel<<<1, 1024, 0, st>>>(gamma, labels, B, loss);
+    count_launch();
+  }
+  return check_last();
+}
+
+extern "C" int spex_bce_bwd_f32(const float* U, const float* I, int32_t D, const int64_t* users,
+                                const int64_t* items, const float* dgamma, const float* grad_loss,
+                                int64_t B, float* gU, float* gI, void* stream) {
+  SPEX_RETURN_IF(!U || !I || !users || !items || !dgamma || !gU || !gI || B < 0, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I) || !aligned16(gU) || !aligned16(gI), SPEX_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  ScatterList L{};
+  L.nseg = 1;
+  L.B = B;
+  L.coef = dgamma;
+  L.gscalar = grad_loss;
+  L.cconst = 1.f;
+  L.sign[0] = 1.f;
+  // gU[users] += dgamma * I[items]
+  L.idx[0] = users;
+  L.src_idx[0] = items;
+  int rc = launch_scatter(L, I, gU, D, st);
+  if (rc) return rc;
+  // gI[items] += dgamma * U[users]
+  L.idx[0] = items;
+  L.src_idx[0] = users;
+  return launch_scatter(L, U, gI, D, st);
+}
+
+extern "C" int spex_bpr_fwd_f32(const float* U, const float* I, const float* U0, const float* I0,
+                                int32_t D, const int64_t* users, const int64_t* pos,
+                                const int64_t* neg, int64_t B, float* out2, float* dscore,
+                                float* work2B, void* stream) {
+  SPEX_RETURN_IF(!U || !I || !U0 || !I0 || !users || !pos || !neg || !out2 || !work2B || B < 0,
+                 SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I) || !aligned16(U0) || !aligned16(I0), SPEX_E_ALIGN);
+  SPEX_RETURN_IF(B > 0x7fffffffLL, SPEX_E_TOOBIG);
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D <= 128)
+    bpr_fwd_kernel<1><<<warp_grid(B), kWarpsPerCta * 32, 0, st>>>(U, I, U0, I0, D, users, pos, neg, B, dscore, work2B);
+  else
+    bpr_fwd_kernel<4><<<warp_grid(B), kWarpsPerCta * 32, 0, st>>>(U, I, U0, I0, D, users, pos, neg, B, dscore, work2B);
+  pair_mean_reduce_kernel<<<1, 1024, 0, st>>>(work2B, B, out2);
+  count_launch(2);
+  return check_last();
+}
+
+extern "C" int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const float* I0,
+                                int32_t D, const int64_t* users, const int64_t* pos,
+                                const int64_t* neg, const float* dscore, const float* grad2,
+                                int64_t B, float* gU, float* gI, float* gU0, float* gI0,
+                                void* stream) {
+  SPEX_RETURN_IF(!U || !I || !U0 || !I0 || !users || !pos || !neg || !dscore || B < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(!gU || !gI || !gU0 || !gI0, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I) || !aligned16(U0) || !aligned16(I0), SPEX_E_ALIGN);
+  SPEX_RETURN_IF(!aligned16(gU) || !aligned16(gI) || !aligned16(gU0) || !aligned16(gI0), SPEX_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  ScatterList L{};
+  L.B = B;
+  L.cconst = 1.f;
+  // propagated tables: upstream dL/dloss = grad2[0]
+  L.coef = dscore;
+  L.gscalar = grad2;
+  // gU[u] = sum d * (I[neg] - I[pos])   (pos terms first, then neg: fixed order)
+  L.nseg = 2;
+  L.idx[0] = users; L.src_idx[0] = pos; L.sign[0] = -1.f;
+  L.idx[1] = users; L.src_idx[1] = neg; L.sign[1] = 1.f;
+  if ((rc = launch_scatter(L, I, gU, D, st))) return rc;
+  // gI[pos] -= d*U[u];  gI[neg] += d*U[u]
+  L.idx[0] = pos; L.src_idx[0] = users; L.sign[0] = -1.f;
+  L.idx[1] = neg; L.src_idx[1] = users; L.sign[1] = 1.f;
+  if ((rc = launch_scatter(L, U, gI, D, st))) return rc;
+  // ego tables: reg = 0.5*sum|.|^2 / B  ->  d/dx = x / B, times upstream grad2[1]
+  L.coef = nullptr;
+  L.gscalar = grad2 ? grad2 + 1 : nullptr;
+  L.cconst = 1.f / (float)(B > 0 ? B : 1);
+  L.nseg = 1;
+  L.idx[0] = users; L.src_idx[0] = users; L.sign[0] = 1.f;
+  if ((rc = launch_scatter(L, U0, gU0, D, st))) return rc;
+  L.nseg = 2;
+  L.idx[0] = pos; L.src_idx[0] = pos; L.sign[0] = 1.f;
+  L.idx[1] = neg; L.src_idx[1] = neg; L.sign[1] = 1.f;
+  return launch_scatter(L, I0, gI0, D, st);
+}
+
+extern "C" int spex_adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float beta1, float beta2, float eps, int32_t step, void* stream) {
+  SPEX_RETURN_IF(!p || !g || !m || !v || n < 0 || step < 1, SPEX_E_BADARG);
+  SPEX_RETURN_IF(!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v), SPEX_E_ALIGN);
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const int64_t n4 = n / 4;
+  const int ntail = (int)(n - n4 * 4);
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n4, beta1, beta2, eps, step_size,
+      bc2_sqrt, p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, ntail);
+  count_launch();
+  return check_last();
+}
+
+extern "C" int spex_expert_gate_f32(const float* E0, const float* Eout, const float* W, int64_t n,
+                                    int32_t D, float* out, void* stream) {
+  SPEX_RETURN_IF(!E0 || !Eout || !W || !out || n < 0, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(E0) || !aligned16(Eout) || !aligned16(out) || ((uintptr_t)W & 7), SPEX_E_ALIGN);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D <= 128)
+    expert_gate_kernel<1><<<warp_grid(n), kWarpsPerCta * 32, 0, st>>>(E0, Eout, W, n, D, out);
+  else
+    expert_gate_kernel<4><<<warp_grid(n), kWarpsPerCta * 32, 0, st>>>(E0, Eout, W, n, D, out);
+  count_launch();
+  return check_last();
+}
+
+extern "C" int spex_score_candidates_f32(const float* U, const float* I, int32_t D,
+                                         const int64_t* users, const int32_t* cand, int64_t n_u,
+                                         int32_t n_c, float* score, void* stream) {
+  SPEX_RETURN_IF(!U || !I || !users || !cand || !score || n_u < 0 || n_c < 0, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I), SPEX_E_ALIGN);
+  const int64_t total = n_u * (int64_t)n_c;
+  if (total == 0) return 0;
+  SPEX_RETURN_IF(total > 0x7fffffffLL * kWarpsPerCta, SPEX_E_TOOBIG);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D <= 128)
+    score_candidates_kernel<1><<<warp_grid(total), kWarpsPerCta * 32, 0, st>>>(U, I, D, users, cand, n_u, n_c, score);
+  else
+    score_candidates_kernel<4><<<warp_grid(total), kWarpsPerCta * 32, 0, st>>>(U, I, D, users, cand, n_u, n_c, score);
+  count_launch();
+  return check_last();
+}

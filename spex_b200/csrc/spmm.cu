@@ -1,0 +1,425 @@
+// spmm.cu — deterministic CSR row-per-warp SpMM for the LightGCN propagation (sm_100a).
+//
+// Replaces torch.sparse.mm(g_droped, all_emb)      LightGCN_SPEX/code/utility1/model.py:91
+// and, through the fused epilogue, stack+mean       model.py:94-95
+// and the autograd of both                          main_rec.py:35
+//
+// Design (HBM-bandwidth kernel, 0.48 flop/B — no tensor cores on purpose):
+//   * one warp owns one output row; the row's (col,val) run is read coalesced, 32 edges at a
+//     time, with streaming cache hints (read-once), and broadcast by warp shuffles;
+//   * a 256-byte embedding row (D=64 fp32) is fetched by 16 lanes x 128-bit, so one LDG.128
+//     warp instruction gathers G=2 neighbour rows; U of those are issued back to back before the
+//     first FMA (U*G rows = U*512 B in flight per warp);
+//   * lane groups accumulate disjoint edge subsets in edge order and are combined by a fixed
+//     xor-shuffle tree: the summation order is a pure function of the row => bit-reproducible,
+//     no atomics;
+//   * rows longer than plan->seg_len are skipped here and reduced by two extra launches
+//     (warp per segment -> partial rows -> warp per long row), again in a fixed order;
+//   * epilogue: Y = acc (next layer's input) and/or Z = (addend*a + acc)*b (running layer mean
+//     forward, g + A^T G backward).  The last layer writes only Z.
+#include "common.cuh"
+
+namespace spex {
+
+int64_t g_launches = 0;
+
+template <int D>
+struct RowShape {
+  static_assert(D == 32 || D == 64 || D == 128, "vector path supports D in {32,64,128}");
+  static constexpr int LPR = D / 4;    // lanes that cover one row with float4
+  static constexpr int G = 32 / LPR;   // neighbour rows gathered per LDG.128 warp instruction
+};
+
+// Sum over edges e in [start,end) of val[e] * X[col[e], :], returned in every lane for the
+// float4 slot `lane % LPR`.  kIdentity: col[e] = e, val[e] = 1 (used to sum partial rows).
+template <int D, int U, bool kIdentity>
+__device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict__ col,
+                                                      const float* __restrict__ val,
+                                                      const float* __restrict__ X, int64_t start,
+                                                      int64_t end, int lane) {
+  constexpr int LPR = RowShape<D>::LPR, G = RowShape<D>::G;
+  const int grp = lane / LPR, sub = lane % LPR;
+  const float* Xs = X + sub * 4;
+  float4 acc = f4_zero();
+  for (int64_t base = start; base < end; base += 32) {
+    const int64_t e = base + lane;
+    int c = 0;
+    float v = 0.f;
+    if (e < end) {
+      if (kIdentity) {
+        c = (int)e;
+        v = 1.f;
+      } else {
+        c = ld_stream_s32(col + e);
+        v = ld_stream_f32(val + e);
+      }
+    }
+    const int n = (int)((end - base) < 32 ? (end - base) : 32);
+#pragma unroll 1
+    for (int j = 0; j < n; j += G * U) {
+      float4 x[U];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = j + u * G + grp;
+        const int cc = __shfl_sync(kFull, c, idx & 31);
+        vv[u] = __shfl_sync(kFull, v, idx & 31);
+        if (idx < n) {
+          x[u] = ld_gather_f4(Xs + (int64_t)cc * D);
+        } else {
+          x[u] = f4_zero();
+          vv[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) f4_fma(acc, vv[u], x[u]);
+    }
+  }
+#pragma unroll
+  for (int m = LPR; m < 32; m <<= 1) f4_add(acc, f4_shfl_xor(acc, m));
+  return acc;
+}
+
+struct Epilogue {
+  float* Y;
+  const float* addend;
+  float addend_scale;
+  float* Z;
+  float z_scale;
+  // optional peer tables (fused all-gather: the Y row is also stored into every peer's copy)
+  float* peer[8];
+  int n_peers;
+  int64_t peer_row_offset;
+};
+
+template <int D>
+__device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int64_t row, int lane) {
+  constexpr int LPR = RowShape<D>::LPR;
+  if (lane < LPR) {
+    const int64_t off = row * D + lane * 4;
+    if (ep.Y) *reinterpret_cast<float4*>(ep.Y + off) = acc;
+    if (ep.n_peers > 0) {
+      const int64_t poff = (row + ep.peer_row_offset) * D + lane * 4;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p < ep.n_peers) *reinterpret_cast<float4*>(ep.peer[p] + poff) = acc;
+    }
+    if (ep.Z) {
+      float4 a = f4_zero();
+      if (ep.addend) a = ld_f4(ep.addend + off);
+      float4 z;
+      z.x = (a.x * ep.addend_scale + acc.x) * ep.z_scale;
+      z.y = (a.y * ep.addend_scale + acc.y) * ep.z_scale;
+      z.z = (a.z * ep.addend_scale + acc.z) * ep.z_scale;
+      z.w = (a.w * ep.addend_scale + acc.w) * ep.z_scale;
+      *reinterpret_cast<float4*>(ep.Z + off) = z;
+    }
+  }
+}
+
+constexpr int kRowsPerCta = 8;  // 8 warps = 256 threads
+
+template <int D, int U>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                 const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
+                 int32_t skip_longer_than, Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int64_t start = rowptr[row], end = rowptr[row + 1];
+  if (skip_longer_than > 0 && end - start > skip_longer_than) return;  // long-row path
+  const float4 acc = warp_row_accumulate<D, U, false>(col, val, X, start, end, lane);
+  row_epilogue<D>(ep, acc, row, lane);
+}
+
+// warp per segment of a long row -> partial[seg, :]
+template <int D, int U>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const float* __restrict__ val, const float* __restrict__ X,
+                     const int32_t* __restrict__ long_rows,
+                     const int32_t* __restrict__ long_segptr, int32_t n_long, int32_t n_seg,
+                     int32_t seg_len, float* __restrict__ partial) {
+  constexpr int LPR = RowShape<D>::LPR;
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  // largest r with long_segptr[r] <= seg
+  int lo = 0, hi = n_long;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (long_segptr[mid] <= seg) lo = mid; else hi = mid;
+  }
+  const int64_t row = long_rows[lo];
+  const int k = seg - long_segptr[lo];
+  const int64_t rs = rowptr[row], re = rowptr[row + 1];
+  const int64_t start = rs + (int64_t)k * seg_len;
+  const int64_t end = (start + seg_len < re) ? start + seg_len : re;
+  const float4 acc = warp_row_accumulate<D, U, false>(col, val, X, start, end, lane);
+  if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
+}
+
+// warp per long row: sum its partial rows in segment order, then the usual epilogue
+template <int D, int U>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
+                     const int32_t* __restrict__ long_segptr, int32_t n_long,
+                     const float* __restrict__ partial, Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (r >= n_long) return;
+  const float4 acc = warp_row_accumulate<D, U, true>(nullptr, nullptr, partial, long_segptr[r],
+                                                     long_segptr[r + 1], lane);
+  row_epilogue<D>(ep, acc, (int64_t)long_rows[r], lane);
+}
+
+// ---- generic D (multiple of 4, <= 512): one edge per step, lane owns float4 slots lane+32*v ----
+template <int NV>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_rows_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                         const float* __restrict__ val, const float* __restrict__ X,
+                         int64_t n_rows, int32_t D, Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int64_t start = rowptr[row], end = rowptr[row + 1];
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = f4_zero();
+  for (int64_t base = start; base < end; base += 32) {
+    const int64_t e = base + lane;
+    int c = 0;
+    float w = 0.f;
+    if (e < end) {
+      c = ld_stream_s32(col + e);
+      w = ld_stream_f32(val + e);
+    }
+    const int n = (int)((end - base) < 32 ? (end - base) : 32);
+    for (int j = 0; j < n; ++j) {
+      const int cc = __shfl_sync(kFull, c, j);
+      const float ww = __shfl_sync(kFull, w, j);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int d = (lane + 32 * v) * 4;
+        if (d < D) f4_fma(acc[v], ww, ld_gather_f4(X + (int64_t)cc * D + d));
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    if (d < D) {
+      const int64_t off = row * D + d;
+      if (ep.Y) *reinterpret_cast<float4*>(ep.Y + off) = acc[v];
+      for (int p = 0; p < ep.n_peers; ++p)
+        *reinterpret_cast<float4*>(ep.peer[p] + (row + ep.peer_row_offset) * D + d) = acc[v];
+      if (ep.Z) {
+        float4 a = f4_zero();
+        if (ep.addend) a = ld_f4(ep.addend + off);
+        float4 z;
+        z.x = (a.x * ep.addend_scale + acc[v].x) * ep.z_scale;
+        z.y = (a.y * ep.addend_scale + acc[v].y) * ep.z_scale;
+        z.z = (a.z * ep.addend_scale + acc[v].z) * ep.z_scale;
+        z.w = (a.w * ep.addend_scale + acc[v].w) * ep.z_scale;
+        *reinterpret_cast<float4*>(ep.Z + off) = z;
+      }
+    }
+  }
+}
+
+template <int D, int U>
+static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                      int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
+                      cudaStream_t st) {
+  const bool has_long = plan && plan->n_long > 0;
+  const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
+  spmm_rows_kernel<D, U><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+      rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep);
+  count_launch();
+  if (has_long) {
+    const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
+    spmm_long_seg_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
+        rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
+        plan->seg_len, plan->partial);
+    const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;
+    spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
+        plan->long_rows, plan->long_segptr, plan->n_long, plan->partial, ep);
+    count_launch(2);
+  }
+  return check_last();
+}
+
+int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                int64_t n_rows, int32_t D, const Epilogue& ep, const spex_long_plan* plan,
+                cudaStream_t st) {
+  SPEX_RETURN_IF(!rowptr || !X || n_rows < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_rows > 0 && (!col || !val), SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
+  SPEX_RETURN_IF(!aligned16(X) || !aligned16(ep.Y) || !aligned16(ep.Z) || !aligned16(ep.addend),
+                 SPEX_E_ALIGN);
+  if (plan && plan->n_long > 0) {
+    SPEX_RETURN_IF(plan->seg_len < 32 || !plan->long_rows || !plan->long_segptr ||
+                       !plan->partial || plan->n_seg < plan->n_long,
+                   SPEX_E_BADARG);
+    SPEX_RETURN_IF(!aligned16(plan->partial), SPEX_E_ALIGN);
+  }
+  if (n_rows == 0) return 0;
+  switch (D) {
+    case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st);
+    case 64: return launch_vec<64, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
+    case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
+    default: break;
+  }
+  // generic path handles long rows serially (no plan needed; still deterministic)
+  const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
+  const int nv = (D + 127) / 128;
+  switch (nv) {
+    case 1: spmm_rows_generic_kernel<1><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(rowptr, col, val, X, n_rows, D, ep); break;
+    case 2: spmm_rows_generic_kernel<2><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(rowptr, col, val, X, n_rows, D, ep); break;
+    case 3: spmm_rows_generic_kernel<3><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(rowptr, col, val, X, n_rows, D, ep); break;
+    default: spmm_rows_generic_kernel<4><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(rowptr, col, val, X, n_rows, D, ep); break;
+  }
+  count_launch();
+  return check_last();
+}
+
+// scale-copy used for K == 0 (out = E0) and the K == 0 backward (dE0 = g)
+__global__ void copy_f4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) dst[i] = src[i];
+}
+
+__global__ void gather_scale_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                    const float* __restrict__ scale, float* __restrict__ out,
+                                    int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = idx ? src[idx[i]] : src[i];
+    if (scale) v *= scale[i];
+    out[i] = v;
+  }
+}
+
+}  // namespace spex
+
+using namespace spex;
+
+extern "C" int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                                 const float* X, int64_t n_rows, int32_t D, float* Y,
+                                 const float* addend, float addend_scale, float* Z, float z_scale,
+                                 const spex_long_plan* plan, void* stream) {
+  Epilogue ep{};
+  ep.Y = Y;
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.n_peers = 0;
+  ep.peer_row_offset = 0;
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,
+                                      const float* X, int64_t n_rows, int32_t D,
+                                      int64_t out_row_offset, float* const* peer_Y_host,
+                                      int32_t n_peers, const float* addend, float addend_scale,
+                                      float* Z, float z_scale, const spex_long_plan* plan,
+                                      void* stream) {
+  SPEX_RETURN_IF(n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_Y_host), SPEX_E_BADARG);
+  Epilogue ep{};
+  ep.Y = nullptr;
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.n_peers = n_peers;
+  ep.peer_row_offset = out_row_offset;
+  for (int p = 0; p < n_peers; ++p) {
+    SPEX_RETURN_IF(!peer_Y_host[p] || !aligned16(peer_Y_host[p]), SPEX_E_BADARG);
+    ep.peer[p] = peer_Y_host[p];
+  }
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+extern "C" int spex_propagate_mean_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                                       const float* E0, int64_t N, int32_t D, int32_t K, float* out,
+                                       float* tmp0, float* tmp1, const spex_long_plan* plan,
+                                       void* stream) {
+  SPEX_RETURN_IF(!E0 || !out || N < 0 || K < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
+  SPEX_RETURN_IF((K >= 2 && !tmp0) || (K >= 3 && !tmp1), SPEX_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) return 0;
+  if (K == 0) {
+    SPEX_RETURN_IF(!aligned16(E0) || !aligned16(out), SPEX_E_ALIGN);
+    copy_f4_kernel<<<1184, 256, 0, st>>>((const float4*)E0, (float4*)out, N * D / 4);
+    count_launch();
+    return check_last();
+  }
+  const float inv = 1.0f / (float)(K + 1);
+  float* tmp[2] = {tmp0, tmp1};
+  const float* X = E0;
+  for (int k = 0; k < K; ++k) {
+    const bool last = (k == K - 1);
+    Epilogue ep{};
+    ep.Y = last ? nullptr : tmp[k & 1];
+    ep.addend = (k == 0) ? E0 : out;
+    ep.addend_scale = 1.f;
+    ep.Z = out;
+    ep.z_scale = last ? inv : 1.f;
+    int rc = spmm_launch(rowptr, col, val, X, N, D, ep, plan, st);
+    if (rc) return rc;
+    X = tmp[k & 1];
+  }
+  return 0;
+}
+
+extern "C" int spex_propagate_mean_bwd_f32(const int64_t* rowptr, const int32_t* col,
+                                           const float* valT, const float* g, int64_t N, int32_t D,
+                                           int32_t K, float* dE0, float* tmp0, float* tmp1,
+                                           const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(!g || !dE0 || N < 0 || K < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
+  SPEX_RETURN_IF((K >= 2 && !tmp0) || (K >= 3 && !tmp1), SPEX_E_BADARG);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) return 0;
+  if (K == 0) {
+    SPEX_RETURN_IF(!aligned16(g) || !aligned16(dE0), SPEX_E_ALIGN);
+    copy_f4_kernel<<<1184, 256, 0, st>>>((const float4*)g, (float4*)dE0, N * D / 4);
+    count_launch();
+    return check_last();
+  }
+  // H_K = g; H_k = g + A^T H_{k+1}; dE0 = H_0 / (K+1)
+  const float inv = 1.0f / (float)(K + 1);
+  float* tmp[2] = {tmp0, tmp1};
+  const float* X = g;
+  for (int j = 1; j <= K; ++j) {
+    const bool last = (j == K);
+    Epilogue ep{};
+    ep.Y = nullptr;
+    ep.addend = g;
+    ep.addend_scale = 1.f;
+    ep.Z = last ? dE0 : tmp[(j - 1) & 1];
+    ep.z_scale = last ? inv : 1.f;
+    int rc = spmm_launch(rowptr, col, valT, X, N, D, ep, plan, st);
+    if (rc) return rc;
+    X = tmp[(j - 1) & 1];
+  }
+  return 0;
+}
+
+extern "C" int spex_gather_f32(const float* src, const int64_t* idx, const float* scale, float* out,
+                               int64_t n, void* stream) {
+  SPEX_RETURN_IF(!src || !out || n < 0, SPEX_E_BADARG);
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, scale, out, n);
+  count_launch();
+  return check_last();
+}
