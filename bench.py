@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — LightGCN_SPEX propagation throughput (GEdges/s) + full-rank top-20 users/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+
+One "step" = one computer() forward of the reference model
+(/root/reference/LightGCN_SPEX/code/utility1/model.py:66-97): K_layers = 3 propagation layers over
+the normalised adjacency + layer mean, D = 64, fp32.  Workload (BASELINE.json configs[3]): synthetic
+10 M users x 5 M items, ~10^9 interaction edges => nnz(A) ~ 2*10^9 (both directions are stored and
+processed, dataloader.py:200-201).  Metric: GEdges/s = nnz(A) * K_layers / t_step, whole job.
+
+N > 1 (torchrun, one rank per GPU): the graph is row-partitioned by nnz, each layer ends with an
+exchange of the embedding slices over NVLink (strong scaling: the graph is fixed).
+
+JSON keys beyond the base contract:
+  roofline      dominant kernel (CSR SpMM): algorithmic bytes per launch (nnz+N)*264
+                / CUDA-event time per launch, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (torch.sparse.mm path, the reference's own backend) on a bounded sample
+  e2e           same metric through the public API with HOST tables: H2D of the fused embedding
+                table and D2H of the propagated table inside the timed region
+  eval          secondary metric: full-ranking top-20 users/s (tcgen05 scoring GEMM + mask + top-k)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G_USERS, G_ITEMS, G_INTER = 10_000_000, 5_000_000, 1_000_000_000
+D, K_LAYERS, TOPK = 64, 3, 20
+METRIC, UNIT = "lightgcn_propagation_gedges_per_s", "GEdges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10M x 5M x 1B workload")
+    ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "push"), choices=["nccl", "push"])
+    ap.add_argument("--eval-users", type=int, default=148 * 128 * 2)
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-scale", type=float, default=0.01)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], j["bf16_tflops"], j.get("bf16_tflops_sustained", j["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def workload(scale):
+    return (max(int(G_USERS * scale), 1000), max(int(G_ITEMS * scale), 500),
+            max(int(G_INTER * scale), 10000))
+
+
+# ---- clocks sampling ---------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+        self.t0 = self.t1 = None
+
+    def mark(self, start):
+        if start:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            # the sampler runs over the whole timed phase; under-load samples dominate the upper half
+            s = sorted(sm)
+            out["sm_mhz"] = s[len(s) // 2]
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---- CPU legs (oracle = the reference's torch CPU path restated; the checker, not the product) -------
+def cpu_sample_graph(scale):
+    import numpy as np
+    from oracle import lightgcn_oracle as O
+
+    nu, m, ni = workload(scale)
+    u, i = O.random_bipartite(nu, m, ni, 2020)
+    A = O.to_sparse_tensor(O.norm_adj_scipy(u, i, nu + 1, m))
+    return A, nu, m
+
+
+def cpu_time_computer(A, nu, m, steps, warmup):
+    import torch
+    from oracle import lightgcn_oracle as O
+
+    torch.manual_seed(2020)
+    uw = torch.empty(nu + 1, D)
+    iw = torch.empty(m, D)
+    torch.nn.init.xavier_uniform_(uw)
+    torch.nn.init.xavier_uniform_(iw)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.computer(uw, iw, A, K_LAYERS)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.computer(uw, iw, A, K_LAYERS)
+        dt = (time.perf_counter() - t0) / steps
+    return A._nnz() * K_LAYERS / dt / 1e9, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port of
+    model.py:66-97, same torch.sparse.mm backend) on all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    A, nu, m = cpu_sample_graph(args.cpu_sample_scale)
+    ge, dt = cpu_time_computer(A, nu, m, args.steps, max(args.warmup, 1))
+    sample = (f"computer() K={K_LAYERS} D={D} on {nu} users x {m} items, nnz(A)={A._nnz()} "
+              f"({args.cpu_sample_scale:g} of the 10Mx5Mx1B workload), uniform synthetic")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ge, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cpu sample of synthetic 10M users x 5M items, 1B interactions, D=64, K=3",
+                   "sample": sample},
+        "cpu_baseline": {"value": ge, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ge, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm -----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from spex_b200 import ops, synthetic
+    from spex_b200 import _capi
+    from spex_b200.dist import PartitionedPropagator
+    from spex_b200.graph import partition_rows_by_nnz
+
+    _capi.device_check()
+    hbm_peak, tc_burst, tc_sust, peak_kind = peaks()
+    nu, m, ni = workload(args.scale)
+    nur = nu + 1
+    N = nur + m
+
+    t_gen = time.time()
+    keys = synthetic.generate_interactions(nu, m, ni, seed=2020, device=dev)
+    g, mask_rp, mask_col = synthetic.build_norm_adj_device(keys, nu, m)
+    del keys
+    nnz = g.nnz
+    table = synthetic.xavier_table(nur, m, D, 2020, dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+
+    launches0 = _capi.launch_count()
+    clocks = Clocks(local_rank) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- propagation: device-resident ----
+    if world == 1:
+        out = torch.empty_like(table)
+        tmp0, tmp1 = torch.empty_like(table), torch.empty_like(table)
+
+        def step():
+            _capi.call("spex_propagate_mean_f32", _capi.ptr(g.rowptr), _capi.ptr(g.col), _capi.ptr(g.val),
+                       _capi.ptr(table), N, D, K_LAYERS, _capi.ptr(out), _capi.ptr(tmp0), _capi.ptr(tmp1),
+                       g.plan(D), _capi.stream_ptr())
+            return out
+        local_nnz = nnz
+        local_rows = N
+        prop = None
+    else:
+        rp_host = g.rowptr.cpu().numpy()
+        bounds = partition_rows_by_nnz(rp_host, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        lo, hi = int(rp_host[r0]), int(rp_host[r1])
+        lg = ops.DeviceGraph((g.rowptr[r0: r1 + 1] - lo).contiguous(), g.col[lo:hi].clone(),
+                             g.val[lo:hi].clone(), N, None, g.seg_len, row_offset=r0)
+        E0_local = table[r0:r1].clone()
+        del g, table
+        torch.cuda.empty_cache()
+        prop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
+        local_nnz, local_rows = hi - lo, r1 - r0
+
+        def step():
+            return prop.propagate(E0_local)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if clocks:
+        clocks.mark(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = nnz * K_LAYERS / (ms_step * 1e-3) / 1e9
+    launches_timed = _capi.launch_count() - launches0
+    launches_per_step = launches_timed // max(args.warmup + args.steps, 1)
+
+    # roofline of the dominant kernel (CSR SpMM), per launch = one layer over this rank's rows.
+    # Algorithmic bytes per layer: every edge reads col(4)+val(4)+one 256 B row,
+    # every row reads rowptr(8) and writes/reads D*4 of output: (nnz + rows) * 264.
+    alg_bytes = (local_nnz + local_rows) * (8 + 4 * D)
+    t_launch = ms_step * 1e-3 / K_LAYERS
+    achieved = alg_bytes / t_launch / 1e9
+    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8> (+long-row passes)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_kind": peak_kind,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "per-launch time = step time / K (exchange included at N>1)"}
+
+    # ---- e2e: host tables in, host tables out, through the public operator ----
+    e2e = None
+    if not args.no_e2e:
+        rows = N if world == 1 else local_rows
+        h_in = torch.empty(rows, D, dtype=torch.float32).pin_memory()
+        h_in.copy_((table if world == 1 else E0_local).cpu())
+        h_out = torch.empty(rows, D, dtype=torch.float32).pin_memory()
+        d_in = table if world == 1 else E0_local
+
+        def e2e_step():
+            d_in.copy_(h_in, non_blocking=True)
+            r = step()
+            h_out.copy_(r, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        n_e2e = max(3, args.steps // 2)
+        ev0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / n_e2e
+        e2e = {"value": nnz * K_LAYERS / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,  # summed over ranks
+               "ms_per_step": ms_e2e, "steps": n_e2e}
+    if clocks:
+        clocks.mark(False)
+
+    # ---- secondary: full-ranking top-20 (users sharded by rank, no communication) ----
+    evalj = None
+    if not args.no_eval:
+        if world == 1:
+            U_all, I_all = res[:nur], res[nur:]
+        else:
+            # every rank needs all propagated item rows: gather once (evaluation set-up, untimed)
+            full = torch.empty(N, D, dtype=torch.float32, device=dev)
+            prop._all_gather_rows(full, res)
+            U_all, I_all = full[:nur], full[nur:]
+        n_eval = min(args.eval_users, nu)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7 + rank)
+        users = torch.randint(0, nu, (n_eval,), device=dev, generator=gen)
+        Ib, m_pad = ops.pack_bf16(I_all, None, 256)
+        idx = torch.empty(n_eval, TOPK, dtype=torch.int32, device=dev)
+        val = torch.empty(n_eval, TOPK, dtype=torch.float32, device=dev)
+
+        def eval_step():
+            Ub, b_pad = ops.pack_bf16(U_all, users, 128)
+            ops.score_topk_bf16(Ub, n_eval, b_pad, Ib, m, m_pad, TOPK, users, mask_rp, mask_col, idx, val)
+
+        eval_step()
+        barrier()
+        n_ev = 3
+        ev0.record()
+        for _ in range(n_ev):
+            eval_step()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ev = float(t.item()) / n_ev
+        flops = 2.0 * n_eval * m * D
+        tf = flops / (ms_ev * 1e-3) / 1e12
+        evalj = {"metric": "fullrank_top20_users_per_s", "value": n_eval * world / (ms_ev * 1e-3),
+                 "unit": "users/s", "users_per_step_per_gpu": n_eval, "m_items": m, "ms_per_step": ms_ev,
+                 "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": tf,
+                              "peak": tc_burst, "unit": "TFLOP/s", "frac": tf / tc_burst,
+                              "peak_kind": peak_kind, "traffic": None}}
+
+    launches_total = _capi.launch_count() - launches0
+    ck = clocks.stop() if clocks else None
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        A, snu, sm_ = cpu_sample_graph(args.cpu_sample_scale)
+        ge, dt = cpu_time_computer(A, snu, sm_, 3, 1)
+        cpu = {"value": ge, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle computer() (torch.sparse.mm, the reference's CPU backend) K={K_LAYERS} D={D} "
+                         f"on {snu} users x {sm_} items, nnz(A)={A._nnz()}, 3 timed runs, {dt * 1e3:.0f} ms each"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {nu} users x {m} items, {nnz // 2} unique interactions "
+                                   f"(nnz(A)={nnz}), D={D}, K={K_LAYERS} (BASELINE.json configs[3], scale {args.scale:g})",
+                       "edges_definition": "nnz(A) = 2*|R| per layer", "l2": "inputs larger than L2 (no flush needed)"
+                       if nnz * 8 > 200e6 else "inputs smaller than L2: timing is L2-warm",
+                       "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" if world > 1 else ""),
+                       "graph_build_s": round(t_gen, 2)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj,
+            "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
+        }
+        print(json.dumps(line), flush=True)
+    if prop is not None:
+        prop.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,10 +99,11 @@ int spex_propagate_mean_bwd_f32(const int64_t* rowptr, const int32_t* col, const
                                 float* dE0, float* tmp0, float* tmp1,
                                 const spex_long_plan* plan, void* stream);
 
-/* out[i] = src[idx[i]] * scale[i]  (scale may be NULL).  Used for the dropout graph
- * (model.py:46-55: kept values / keep_prob as a per-nnz multiplier) and for A^T values. */
-int spex_gather_f32(const float* src, const int64_t* idx, const float* scale, float* out,
-                    int64_t n, void* stream);
+/* out[i] = (src[idx[i]] * scale[i]) / divisor   (idx NULL = identity, scale NULL = 1).
+ * Used for the dropout graph (model.py:46-55: scale = 0/1 keep mask, divisor = keep_prob, an
+ * IEEE fp32 division exactly like `values[random_index] / keep_prob`) and for A^T values. */
+int spex_gather_f32(const float* src, const int64_t* idx, const float* scale, float divisor,
+                    float* out, int64_t n, void* stream);
 
 /*
  * BCE step (reference loss): gamma[b] = <U[users[b]], I[items[b]]>  (model.py:115-118),
@@ -178,6 +179,15 @@ int spex_score_topk_f32(const float* U, const float* I, int32_t D,
                         const int64_t* users, int64_t B, int64_t m_items,
                         const int64_t* mask_rowptr, const int32_t* mask_col,
                         int32_t k, int32_t* out_idx, float* out_val, void* stream);
+
+/*
+ * Dense rating block (API form of getUsersRating, abstract at utility1/model.py:14-15; the only
+ * user x all-items product in the reference is NGCF_SPEX/code/utility/batch_test.py:158):
+ *   out[b, j] = f(<U[users[b]], I[j]>),  f = sigmoid if apply_sigmoid else identity
+ *   out fp32 [B, m_items] row-major;  B <= 8*65535 per call.
+ */
+int spex_rating_f32(const float* U, const float* I, int32_t D, const int64_t* users, int64_t B,
+                    int64_t m_items, int32_t apply_sigmoid, float* out, void* stream);
 
 /*
  * fp32 [rows, D] -> bf16 (round-to-nearest-even) in the UMMA K-major "no-swizzle" canonical

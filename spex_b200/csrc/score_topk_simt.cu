@@ -112,6 +112,48 @@ score_topk_simt_kernel(const float* __restrict__ U, const float* __restrict__ I,
   }
 }
 
+
+// Dense rating block  out[b, j] = f(<U[users[b]], I[j]>), f = sigmoid or identity: the API form of
+// getUsersRating ([B, m_items] materialised).  Same tiling as the top-k kernel; stores are
+// coalesced along items.
+__global__ void __launch_bounds__(TILE)
+rating_dense_kernel(const float* __restrict__ U, const float* __restrict__ I, int D,
+                    const int64_t* __restrict__ users, int64_t B, int64_t m_items, int apply_sigmoid,
+                    float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* su = smem;  // [TU][D]
+  const int tid = threadIdx.x;
+  const int64_t u0 = (int64_t)blockIdx.y * TU;
+  const int nu = (int)((B - u0) < TU ? (B - u0) : TU);
+  for (int i = tid; i < TU * D; i += TILE) {
+    const int u = i / D, d = i - u * D;
+    su[i] = (u < nu) ? U[users[u0 + u] * D + d] : 0.f;
+  }
+  __syncthreads();
+  const int D4 = D >> 2;
+  for (int64_t j = (int64_t)blockIdx.x * TILE + tid; j < m_items; j += (int64_t)gridDim.x * TILE) {
+    float acc[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) acc[u] = 0.f;
+    const float4* row = reinterpret_cast<const float4*>(I + j * D);
+#pragma unroll 4
+    for (int d4 = 0; d4 < D4; ++d4) {
+      const float4 x = __ldg(row + d4);
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        const float4 w = *reinterpret_cast<const float4*>(su + u * D + d4 * 4);
+        acc[u] = fmaf(x.x, w.x, acc[u]);
+        acc[u] = fmaf(x.y, w.y, acc[u]);
+        acc[u] = fmaf(x.z, w.z, acc[u]);
+        acc[u] = fmaf(x.w, w.w, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+      if (u < nu) out[(u0 + u) * m_items + j] = apply_sigmoid ? 1.f / (1.f + expf(-acc[u])) : acc[u];
+  }
+}
+
 }  // namespace spex
 
 using namespace spex;
@@ -137,6 +179,24 @@ extern "C" int spex_score_topk_f32(const float* U, const float* I, int32_t D, co
   SPEX_RETURN_IF(grid > 0x7fffffffLL, SPEX_E_TOOBIG);
   score_topk_simt_kernel<<<(unsigned)grid, TILE, smem, st>>>(U, I, D, users, B, m_items, mask_rowptr,
                                                             mask_col, k, out_idx, out_val);
+  count_launch();
+  return check_last();
+}
+
+extern "C" int spex_rating_f32(const float* U, const float* I, int32_t D, const int64_t* users,
+                               int64_t B, int64_t m_items, int32_t apply_sigmoid, float* out,
+                               void* stream) {
+  SPEX_RETURN_IF(!U || !I || !users || !out || B < 0 || m_items < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
+  SPEX_RETURN_IF(!aligned16(U) || !aligned16(I), SPEX_E_ALIGN);
+  if (B == 0 || m_items == 0) return 0;
+  const size_t smem = (size_t)TU * D * 4;
+  int64_t gx = (m_items + TILE - 1) / TILE;
+  if (gx > 148 * 8) gx = 148 * 8;
+  const int64_t gy = (B + TU - 1) / TU;
+  SPEX_RETURN_IF(gy > 65535, SPEX_E_TOOBIG);
+  rating_dense_kernel<<<dim3((unsigned)gx, (unsigned)gy), TILE, smem, (cudaStream_t)stream>>>(
+      U, I, D, users, B, m_items, apply_sigmoid, out);
   count_launch();
   return check_last();
 }

@@ -294,13 +294,14 @@ __global__ void copy_f4_kernel(const float4* __restrict__ src, float4* __restric
 }
 
 __global__ void gather_scale_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
-                                    const float* __restrict__ scale, float* __restrict__ out,
-                                    int64_t n) {
+                                    const float* __restrict__ scale, float divisor,
+                                    float* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
     float v = idx ? src[idx[i]] : src[i];
     if (scale) v *= scale[i];
+    if (divisor != 1.f) v = v / divisor;  // IEEE fp32 division, as torch's values / keep_prob
     out[i] = v;
   }
 }
@@ -413,13 +414,13 @@ extern "C" int spex_propagate_mean_bwd_f32(const int64_t* rowptr, const int32_t*
   return 0;
 }
 
-extern "C" int spex_gather_f32(const float* src, const int64_t* idx, const float* scale, float* out,
-                               int64_t n, void* stream) {
-  SPEX_RETURN_IF(!src || !out || n < 0, SPEX_E_BADARG);
+extern "C" int spex_gather_f32(const float* src, const int64_t* idx, const float* scale,
+                               float divisor, float* out, int64_t n, void* stream) {
+  SPEX_RETURN_IF(!src || !out || n < 0 || divisor == 0.f, SPEX_E_BADARG);
   if (n == 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gather_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, scale, out, n);
+  gather_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, scale, divisor, out, n);
   count_launch();
   return check_last();
 }

@@ -1,0 +1,265 @@
+"""LightGCN with the reference's API surface, computed by the sm_100a kernels of libspex_b200.
+
+Drop-in for /root/reference/LightGCN_SPEX/code/utility1/model.py (class LightGCN, lines 19-121):
+same constructor ``LightGCN(args_r, dataset)``, same attributes (``embedding_user``,
+``embedding_item``, ``Graph``, ``num_users``, ``num_items``, ``n_layers``, ``keep_prob``,
+``A_split``, ``f``, ``bcel``), same methods ``computer()`` and ``forward(users, items, labels,
+flag)``, same RNG consumption at construction (so a shared seed gives identical initial weights).
+It adds what BASELINE.json's north_star asks for and the reference leaves abstract or undefined:
+``getUsersRating`` (model.py:14-15 raises NotImplementedError), ``bpr_loss`` and the fused
+full-ranking ``rank_topk``.
+
+Differences in HOW (not in WHAT):
+  * the two embedding tables live in one [n_users+1+m_items, D] buffer, the nn.Embedding weights
+    are views of it: no torch.cat per call (model.py:72);
+  * K layers = K launches of the CSR SpMM, the layer mean rides in the epilogue: no stack/mean
+    temporaries (model.py:94-95);
+  * edge dropout (model.py:46-55) keeps the CSR structure and scales values by mask/keep_prob;
+    the mask is drawn by the same CPU ``torch.rand(nnz)`` call so a shared seed drops the same
+    edges;
+  * the backward is explicit (A^T SpMMs + deterministic segmented scatter), no atomics.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .graph import build_interaction_csr
+
+
+class BasicModel(nn.Module):
+    def getUsersRating(self, users):
+        raise NotImplementedError
+
+
+class _FusedTable(torch.autograd.Function):
+    """Autograd glue: (user_weight, item_weight) -> the fused [N, D] table they are views of."""
+
+    @staticmethod
+    def forward(ctx, user_w, item_w, table):
+        nur = user_w.shape[0]
+        row_bytes = table.shape[1] * table.element_size()
+        fused = (user_w.data_ptr() == table.data_ptr()
+                 and item_w.data_ptr() == table.data_ptr() + nur * row_bytes)
+        if not fused:  # somebody re-pointed a weight: refresh the table (rare path)
+            table[:nur].copy_(user_w)
+            table[nur:].copy_(item_w)
+        ctx.nur = nur
+        return table.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[: ctx.nur], g[ctx.nur:], None
+
+
+class LightGCN(BasicModel):
+    def __init__(self, args_r, dataset):
+        super().__init__()
+        self.args_r = args_r
+        self.dataset = dataset
+        self.bcel = nn.BCEWithLogitsLoss()  # kept for API parity; the fused kernel computes it
+
+        self.num_users = dataset.n_users
+        self.num_items = dataset.m_items
+        self.latent_dim = args_r.recdim
+        self.n_layers = args_r.layer
+        self.keep_prob = args_r.keepprob
+        self.A_split = args_r.A_split
+
+        # same construction order as model.py:32-35 => same RNG stream => same initial weights
+        self.embedding_user = nn.Embedding(self.num_users + 1, self.latent_dim)
+        self.embedding_item = nn.Embedding(self.num_items, self.latent_dim)
+        nn.init.xavier_uniform_(self.embedding_user.weight, gain=1)
+        nn.init.xavier_uniform_(self.embedding_item.weight, gain=1)
+
+        self.f = nn.Sigmoid()
+        self.Graph = dataset.getSparseGraph()
+
+        self._table: Optional[torch.Tensor] = None
+        self._dev_graph: Optional[ops.DeviceGraph] = None
+        self._mask_csr = None
+        self._frozen_out: Optional[torch.Tensor] = None
+        self._freeze = False
+        self._item_pack = None
+        self._fuse()
+
+    # ---- fused table ---------------------------------------------------------------------------
+    @property
+    def n_user_rows(self) -> int:
+        return self.num_users + 1
+
+    def _fuse(self):
+        uw, iw = self.embedding_user.weight, self.embedding_item.weight
+        nur = uw.shape[0]
+        table = torch.empty(nur + iw.shape[0], uw.shape[1], dtype=uw.dtype, device=uw.device)
+        with torch.no_grad():
+            table[:nur].copy_(uw)
+            table[nur:].copy_(iw)
+        uw.data = table[:nur]
+        iw.data = table[nur:]
+        self._table = table
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self._fuse()  # .to()/.cuda() moved the two weights separately: re-fuse on the new device
+        self._dev_graph = None
+        self._mask_csr = None
+        self._frozen_out = None
+        self._item_pack = None
+        return self
+
+    def train(self, mode: bool = True):
+        self._frozen_out = None
+        self._item_pack = None
+        return super().train(mode)
+
+    # ---- graph ---------------------------------------------------------------------------------
+    def device_graph(self) -> ops.DeviceGraph:
+        dev = self.embedding_user.weight.device
+        if self._dev_graph is None or self._dev_graph.device != dev:
+            if dev.type != "cuda":
+                raise RuntimeError("spex_b200.LightGCN computes on sm_100a only: move the model to "
+                                   "a CUDA device (there is no CPU fallback)")
+            host = getattr(self.dataset, "getCSR", None)
+            if host is not None:
+                self._dev_graph = ops.DeviceGraph.from_host(host(), dev, D_hint=self.latent_dim)
+            else:
+                A = self.Graph
+                if isinstance(A, (list, tuple)):  # A_split row folds (dataloader.py:167-177)
+                    A = _stack_row_folds(A)
+                self._dev_graph = ops.DeviceGraph.from_sparse_coo(A, dev)
+        return self._dev_graph
+
+    def _dropout_values(self, g: ops.DeviceGraph):
+        # model.py:50-53: keep edge e iff int(rand[e] + keep_prob) != 0; kept values / keep_prob.
+        # Same CPU generator call as the reference, in coalesced (= CSR) edge order.
+        keep = (torch.rand(g.nnz) + self.keep_prob).int().bool()
+        val = g.dropout_values(keep, self.keep_prob)
+        valT = g.transposed_values(val) if g.tpos is not None else None
+        if valT is None:
+            raise RuntimeError("edge dropout needs the transpose map of the adjacency; build the "
+                               "graph through spex_b200.dataloader (getCSR)")
+        return val, valT
+
+    # ---- propagation ---------------------------------------------------------------------------
+    def _propagate(self) -> torch.Tensor:
+        """[N, D] layer-mean embeddings; rows [0, n_users] users, the rest items."""
+        if self._freeze and self._frozen_out is not None:
+            return self._frozen_out
+        g = self.device_graph()
+        table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
+        val = valT = None
+        if self.args_r.dropout and self.training:
+            val, valT = self._dropout_values(g)
+        out = ops.propagate_mean(table, g, self.n_layers, val, valT)
+        if self._freeze:
+            self._frozen_out = out.detach()
+        return out
+
+    def computer(self):
+        """propagate methods for lightGCN: returns (users [n_users+1, D], items [m_items, D])."""
+        out = self._propagate()
+        return out[: self.n_user_rows], out[self.n_user_rows:]
+
+    @contextlib.contextmanager
+    def frozen_eval(self):
+        """Reuse one propagation across many forward(flag=1) calls (the reference's Test() calls
+        the model once per user, utility1/batch_test.py:33; weights do not change in between)."""
+        if self.training:
+            raise RuntimeError("frozen_eval() is for eval mode")
+        self._freeze, self._frozen_out = True, None
+        try:
+            yield self
+        finally:
+            self._freeze, self._frozen_out = False, None
+
+    # ---- reference forward ---------------------------------------------------------------------
+    def forward(self, users, items, labels, flag=0):
+        if flag not in (0, 1):
+            raise UnboundLocalError("loss")  # the reference falls through to `return loss` unbound
+        out = self._propagate()
+        if flag == 1:
+            return ops.gather_dot(out, self.n_user_rows, users, items)
+        return ops.bce_loss(out, self.n_user_rows, users, items, labels)
+
+    # ---- north_star additions ------------------------------------------------------------------
+    def bpr_loss(self, users, pos, neg):
+        """(loss, reg_loss): mean softplus(<u,n> - <u,p>) and 0.5*(|u0|^2+|p0|^2+|n0|^2)/B with
+        u,p,n from computer() and u0,p0,n0 the raw embedding rows."""
+        out = self._propagate()
+        table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
+        return ops.bpr_loss(out, table, self.n_user_rows, users, pos, neg)
+
+    def getUsersRating(self, users):
+        """sigmoid(out_users[users] . out_items^T) -> [B, m_items] (dense; for ranking use
+        rank_topk, which never materialises this matrix)."""
+        all_users, all_items = self.computer()
+        users = torch.as_tensor(users, device=all_users.device).long()
+        return ops.rating_dense(all_users, all_items, users)
+
+    def train_mask_csr(self):
+        """CSR of the training interactions on the device (rows = user ids): the top-k mask."""
+        if self._mask_csr is None:
+            dev = self.embedding_user.weight.device
+            ds = self.dataset
+            if hasattr(ds, "getInteractionCSR"):
+                rp, col = ds.getInteractionCSR()
+            else:
+                rp, col = build_interaction_csr(ds.trainUser, ds.trainItem, self.n_user_rows,
+                                                self.num_items)
+            self._mask_csr = (torch.as_tensor(rp, dtype=torch.int64).to(dev),
+                              torch.as_tensor(col, dtype=torch.int32).to(dev))
+        return self._mask_csr
+
+    @torch.no_grad()
+    def rank_topk(self, users, k: int = 20, exclude_train: bool = True, precision: str = "bf16",
+                  user_block: int = 1 << 16):
+        """Full-ranking top-k items per user: (idx int32 [B,k], score fp32 [B,k]).
+
+        precision "bf16": tcgen05 GEMM with fused mask + top-k (D must be 64);
+        precision "fp32": exact CUDA-core scorer (bit-exact ordering, any D).
+        Ordering: score descending, ties by ascending item id; masked = the user's train items.
+        """
+        all_users, all_items = self.computer()
+        dev = all_users.device
+        users = torch.as_tensor(users, device=dev).long().contiguous()
+        mrp = mcol = None
+        if exclude_train:
+            mrp, mcol = self.train_mask_csr()
+        if precision == "fp32":
+            return ops.score_topk_f32(all_users, all_items, users, k, mrp, mcol)
+        if precision != "bf16":
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if self.latent_dim != 64:
+            raise RuntimeError("the tcgen05 scorer is built for recdim == 64")
+        if self._item_pack is None or self.training:
+            Ib, m_pad = ops.pack_bf16(all_items, None, 256)
+            self._item_pack = (Ib, m_pad)
+        Ib, m_pad = self._item_pack
+        B = users.numel()
+        idx = torch.empty(B, k, dtype=torch.int32, device=dev)
+        val = torch.empty(B, k, dtype=torch.float32, device=dev)
+        for s in range(0, B, user_block):
+            ub = users[s: s + user_block]
+            Ub, b_pad = ops.pack_bf16(all_users, ub, 128)
+            ops.score_topk_bf16(Ub, ub.numel(), b_pad, Ib, self.num_items, m_pad, k, ub, mrp, mcol,
+                                idx[s: s + ub.numel()], val[s: s + ub.numel()])
+        return idx, val
+
+
+def _stack_row_folds(folds):
+    idx, vals, r0 = [], [], 0
+    n_cols = folds[0].shape[1]
+    for f in folds:
+        f = f.coalesce()
+        i = f.indices().clone()
+        i[0] += r0
+        idx.append(i)
+        vals.append(f.values())
+        r0 += f.shape[0]
+    return torch.sparse_coo_tensor(torch.cat(idx, 1), torch.cat(vals), (r0, n_cols)).coalesce()

@@ -1,0 +1,442 @@
+"""Operators of the LightGCN_SPEX hot path: thin PyTorch host code over the C-ABI (libspex_b200.so).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic step
+below is one of the hand-written sm_100a kernels declared in include/spex_b200.h.  There is no
+CPU or ATen fallback: a CPU tensor raises.
+
+Reference call sites replaced (paths relative to /root/reference/LightGCN_SPEX/code):
+    propagate_mean      utility1/model.py:66-97   (cat + K x torch.sparse.mm + stack + mean)
+    bce_loss/gather_dot utility1/model.py:111-121 (gather, mul, sum, BCEWithLogitsLoss)
+    bpr_loss            north_star addition
+    score_topk*         north_star addition: getUsersRating (model.py:14-15) + top-k
+    score_candidates    utility1/batch_test.py:28-40 (hoisted out of the per-user loop)
+    expert_gate         utility1/model_expert_s.py:154-161
+    adam_step           main_rec.py:23,37
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import LongPlan, call, ptr, stream_ptr
+from .graph import CSRGraph, DEFAULT_SEG_LEN, plan_long_rows
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "spex_b200 runs on sm_100a only: got a CPU tensor (there is no CPU fallback path)"
+            )
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64c(t: torch.Tensor, device) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t))
+    t = t.to(device=device, dtype=torch.int64, non_blocking=True)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class DeviceGraph:
+    """CSR adjacency resident in HBM + long-row plan + (optional) transpose map.
+
+    Layout in HBM: rowptr int64 [n_rows+1], col int32 [nnz], val fp32 [nnz];
+    for the 1B-edge graph that is 16 GB for (col,val) and 120 MB for rowptr.
+    """
+
+    def __init__(self, rowptr, col, val, n_cols: int, tpos=None, seg_len: int = DEFAULT_SEG_LEN,
+                 row_offset: int = 0, symmetric: bool = True, D_hint: int = 64):
+        _need_cuda(rowptr, col, val)
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32 and val.dtype == torch.float32
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_rows = rowptr.numel() - 1
+        self.n_cols = int(n_cols)
+        self.nnz = col.numel()
+        self.tpos = tpos
+        self.row_offset = int(row_offset)
+        self.symmetric = symmetric
+        self.device = val.device
+        self.seg_len = int(seg_len)
+        self._plan_struct = None
+        self._plan_D = 0
+        self._plan_tensors = None
+        self._build_plan(D_hint)
+
+    # -- construction ---------------------------------------------------------------------------
+    @classmethod
+    def from_host(cls, g: CSRGraph, device, seg_len: int = DEFAULT_SEG_LEN, D_hint: int = 64):
+        dev = torch.device(device)
+        rowptr = torch.from_numpy(np.ascontiguousarray(g.rowptr)).to(dev)
+        col = torch.from_numpy(np.ascontiguousarray(g.col)).to(dev)
+        val = torch.from_numpy(np.ascontiguousarray(g.val)).to(dev)
+        tpos = None if g.tpos is None else torch.from_numpy(np.ascontiguousarray(g.tpos)).to(dev)
+        return cls(rowptr, col, val, g.n_cols, tpos, seg_len, g.row_offset, D_hint=D_hint)
+
+    @classmethod
+    def from_sparse_coo(cls, A: torch.Tensor, device, seg_len: int = DEFAULT_SEG_LEN):
+        """From what BasicDataset.getSparseGraph() returns (coalesced COO, int64 indices)."""
+        A = A.coalesce()
+        idx = A.indices()
+        n_rows, n_cols = A.shape
+        dev = torch.device(device)
+        rows = idx[0].to(dev)
+        counts = torch.bincount(rows, minlength=n_rows)
+        rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=rowptr[1:])
+        col = idx[1].to(dev).to(torch.int32)
+        val = A.values().to(dev).to(torch.float32)
+        return cls(rowptr, col, val, n_cols, None, seg_len)
+
+    def _build_plan(self, D: int):
+        rp = self.rowptr.cpu().numpy() if self.n_rows < (1 << 26) else None
+        if rp is None:
+            deg = (self.rowptr[1:] - self.rowptr[:-1])
+            long_rows_t = torch.nonzero(deg > self.seg_len).flatten()
+            nseg = (deg[long_rows_t] + self.seg_len - 1) // self.seg_len
+            segptr = torch.zeros(long_rows_t.numel() + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(nseg, 0, out=segptr[1:])
+            long_rows = long_rows_t.to(torch.int32)
+            segptr = segptr.to(torch.int32)
+        else:
+            lr, sp = plan_long_rows(rp, self.seg_len)
+            long_rows = torch.from_numpy(lr).to(self.device)
+            segptr = torch.from_numpy(sp).to(self.device)
+        self.long_rows, self.long_segptr = long_rows, segptr
+        self.n_long = int(long_rows.numel())
+        self.n_seg = int(segptr[-1].item()) if self.n_long else 0
+        self._plan_D = 0
+
+    def plan(self, D: int):
+        """ctypes pointer to a spex_long_plan for embedding width D (NULL if no long rows)."""
+        if self.n_long == 0:
+            return None
+        if self._plan_D != D:
+            partial = torch.empty(self.n_seg * D, dtype=torch.float32, device=self.device)
+            st = LongPlan(self.seg_len, self.n_long, self.n_seg, 0, self.long_rows.data_ptr(),
+                          self.long_segptr.data_ptr(), partial.data_ptr())
+            self._plan_tensors = partial
+            self._plan_struct = st
+            self._plan_D = D
+        return C.byref(self._plan_struct)
+
+    # -- derived graphs -------------------------------------------------------------------------
+    def with_values(self, val: torch.Tensor, symmetric: bool) -> "DeviceGraph":
+        g = object.__new__(DeviceGraph)
+        g.__dict__.update(self.__dict__)
+        g.val = val
+        g.symmetric = symmetric
+        return g
+
+    def transposed_values(self, val: torch.Tensor) -> torch.Tensor:
+        """valT[e] = val[tpos[e]]: values of A^T laid out on the (symmetric) structure of A."""
+        if self.tpos is None:
+            raise RuntimeError("graph has no transpose map (tpos)")
+        out = torch.empty_like(val)
+        call("spex_gather_f32", ptr(val), ptr(self.tpos), None, 1.0, ptr(out), self.nnz, stream_ptr())
+        return out
+
+    def dropout_values(self, keep_mask: torch.Tensor, keep_prob: float) -> torch.Tensor:
+        """val * mask / keep_prob as a per-nnz multiplier (model.py:46-55 in multiplier form)."""
+        scale = keep_mask.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(self.val)
+        call("spex_gather_f32", ptr(self.val), None, ptr(scale), float(keep_prob), ptr(out), self.nnz,
+             stream_ptr())
+        return out
+
+    def to_sparse_coo(self) -> torch.Tensor:
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), deg)
+        idx = torch.stack([rows + self.row_offset, self.col.to(torch.int64)])
+        return torch.sparse_coo_tensor(idx, self.val, (self.n_rows, self.n_cols), is_coalesced=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def spmm(g: DeviceGraph, X: torch.Tensor, Y: Optional[torch.Tensor] = None,
+         addend: Optional[torch.Tensor] = None, addend_scale: float = 1.0,
+         Z: Optional[torch.Tensor] = None, z_scale: float = 1.0, val: Optional[torch.Tensor] = None):
+    """One layer Y = A.X with the fused epilogue Z = (addend*addend_scale + A.X) * z_scale."""
+    _need_cuda(X)
+    X = _f32c(X)
+    D = X.shape[1]
+    if X.shape[0] != g.n_cols:
+        raise ValueError(f"X has {X.shape[0]} rows, graph has {g.n_cols} columns")
+    if Y is None and Z is None:
+        Y = torch.empty(g.n_rows, D, dtype=torch.float32, device=X.device)
+    v = g.val if val is None else val
+    call("spex_spmm_csr_f32", ptr(g.rowptr), ptr(g.col), ptr(v), ptr(X), g.n_rows, D, ptr(Y),
+         ptr(addend), float(addend_scale), ptr(Z), float(z_scale), g.plan(D), stream_ptr())
+    return Y if Y is not None else Z
+
+
+class _PropagateMean(torch.autograd.Function):
+    """out = mean_k A^k E0 over the fused [N, D] table (model.py:66-97), backward through A^T."""
+
+    @staticmethod
+    def forward(ctx, table, graph: DeviceGraph, K: int, val, valT):
+        _need_cuda(table)
+        E0 = _f32c(table)
+        N, D = E0.shape
+        out = torch.empty_like(E0)
+        tmp0 = torch.empty_like(E0) if K >= 2 else None
+        tmp1 = torch.empty_like(E0) if K >= 3 else None
+        v = graph.val if val is None else val
+        call("spex_propagate_mean_f32", ptr(graph.rowptr), ptr(graph.col), ptr(v), ptr(E0), N, D, K,
+             ptr(out), ptr(tmp0), ptr(tmp1), graph.plan(D), stream_ptr())
+        ctx.graph, ctx.K, ctx.valT = graph, K, (v if valT is None else valT)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        graph, K = ctx.graph, ctx.K
+        g = _f32c(g)
+        N, D = g.shape
+        dE0 = torch.empty_like(g)
+        tmp0 = torch.empty_like(g) if K >= 2 else None
+        tmp1 = torch.empty_like(g) if K >= 3 else None
+        call("spex_propagate_mean_bwd_f32", ptr(graph.rowptr), ptr(graph.col), ptr(ctx.valT), ptr(g),
+             N, D, K, ptr(dE0), ptr(tmp0), ptr(tmp1), graph.plan(D), stream_ptr())
+        return dE0, None, None, None, None
+
+
+def propagate_mean(table: torch.Tensor, graph: DeviceGraph, K: int,
+                   val: Optional[torch.Tensor] = None, valT: Optional[torch.Tensor] = None):
+    """K-layer propagation + layer mean.  `val` overrides the graph values (edge dropout); the
+    backward then needs `valT` (values of the transposed matrix) unless the override is symmetric."""
+    if graph.n_rows != graph.n_cols or table.shape[0] != graph.n_rows:
+        raise ValueError("propagate_mean needs the full square adjacency and an [N, D] table")
+    return _PropagateMean.apply(table, graph, int(K), val, valT)
+
+
+# ------------------------------------------------------------------------------------------------
+class _GatherDot(torch.autograd.Function):
+    """gamma[b] = <out[users[b]], out[n_user_rows + items[b]]>   (model.py:115-118)."""
+
+    @staticmethod
+    def forward(ctx, out, n_user_rows: int, users, items):
+        _need_cuda(out)
+        out = _f32c(out)
+        D = out.shape[1]
+        B = users.numel()
+        gamma = torch.empty(B, dtype=torch.float32, device=out.device)
+        U, I = out[:n_user_rows], out[n_user_rows:]
+        call("spex_bce_fwd_f32", ptr(U), ptr(I), D, ptr(users), ptr(items), None, B, ptr(gamma), None,
+             None, stream_ptr())
+        ctx.save_for_backward(out, users, items)
+        ctx.n_user_rows = n_user_rows
+        return gamma
+
+    @staticmethod
+    def backward(ctx, dgamma):
+        out, users, items = ctx.saved_tensors
+        nur = ctx.n_user_rows
+        D = out.shape[1]
+        g = torch.zeros_like(out)
+        call("spex_bce_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items),
+             ptr(_f32c(dgamma)), None, users.numel(), ptr(g[:nur]), ptr(g[nur:]), stream_ptr())
+        return g, None, None, None
+
+
+class _BCELoss(torch.autograd.Function):
+    """mean BCEWithLogits(<u,i>, label) with the dloss/dgamma produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, out, n_user_rows: int, users, items, labels):
+        _need_cuda(out)
+        out = _f32c(out)
+        D = out.shape[1]
+        B = users.numel()
+        dev = out.device
+        gamma = torch.empty(B, dtype=torch.float32, device=dev)
+        dgamma = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        U, I = out[:n_user_rows], out[n_user_rows:]
+        call("spex_bce_fwd_f32", ptr(U), ptr(I), D, ptr(users), ptr(items), ptr(labels), B, ptr(gamma),
+             ptr(loss), ptr(dgamma), stream_ptr())
+        ctx.save_for_backward(out, users, items, dgamma)
+        ctx.n_user_rows = n_user_rows
+        ctx.mark_non_differentiable(gamma)
+        return loss.reshape(()), gamma
+
+    @staticmethod
+    def backward(ctx, gloss, _ggamma):
+        out, users, items, dgamma = ctx.saved_tensors
+        nur = ctx.n_user_rows
+        D = out.shape[1]
+        g = torch.zeros_like(out)
+        gl = _f32c(gloss.reshape(1))
+        call("spex_bce_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items), ptr(dgamma),
+             ptr(gl), users.numel(), ptr(g[:nur]), ptr(g[nur:]), stream_ptr())
+        return g, None, None, None, None
+
+
+def gather_dot(out, n_user_rows, users, items):
+    dev = out.device
+    return _GatherDot.apply(out, int(n_user_rows), _i64c(users, dev), _i64c(items, dev))
+
+
+def bce_loss(out, n_user_rows, users, items, labels):
+    dev = out.device
+    if not torch.is_tensor(labels):
+        labels = torch.as_tensor(np.asarray(labels))
+    labels = labels.to(device=dev, dtype=torch.float32).contiguous()
+    loss, _ = _BCELoss.apply(out, int(n_user_rows), _i64c(users, dev), _i64c(items, dev), labels)
+    return loss
+
+
+class _BPRLoss(torch.autograd.Function):
+    """(mean softplus(<u,n>-<u,p>), 0.5*(|u0|^2+|p0|^2+|n0|^2)/B)  — north_star bpr_loss."""
+
+    @staticmethod
+    def forward(ctx, out, table, n_user_rows: int, users, pos, neg):
+        _need_cuda(out, table)
+        out, table = _f32c(out), _f32c(table)
+        D = out.shape[1]
+        B = users.numel()
+        dev = out.device
+        out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        dscore = torch.empty(B, dtype=torch.float32, device=dev)
+        work = torch.empty(2 * B, dtype=torch.float32, device=dev)
+        nur = n_user_rows
+        call("spex_bpr_fwd_f32", ptr(out[:nur]), ptr(out[nur:]), ptr(table[:nur]), ptr(table[nur:]), D,
+             ptr(users), ptr(pos), ptr(neg), B, ptr(out2), ptr(dscore), ptr(work), stream_ptr())
+        ctx.save_for_backward(out, table, users, pos, neg, dscore)
+        ctx.n_user_rows = nur
+        return out2[0], out2[1]
+
+    @staticmethod
+    def backward(ctx, gloss, greg):
+        out, table, users, pos, neg, dscore = ctx.saved_tensors
+        nur = ctx.n_user_rows
+        D = out.shape[1]
+        g = torch.zeros_like(out)
+        g0 = torch.zeros_like(table)
+        grad2 = torch.stack([gloss.reshape(()), greg.reshape(())]).to(torch.float32).contiguous()
+        call("spex_bpr_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), ptr(table[:nur]), ptr(table[nur:]), D,
+             ptr(users), ptr(pos), ptr(neg), ptr(dscore), ptr(grad2), users.numel(), ptr(g[:nur]),
+             ptr(g[nur:]), ptr(g0[:nur]), ptr(g0[nur:]), stream_ptr())
+        return g, g0, None, None, None, None
+
+
+def bpr_loss(out, table, n_user_rows, users, pos, neg):
+    dev = out.device
+    return _BPRLoss.apply(out, table, int(n_user_rows), _i64c(users, dev), _i64c(pos, dev),
+                          _i64c(neg, dev))
+
+
+# ------------------------------------------------------------------------------------------------
+def score_candidates(U, I, users, cand):
+    """score[u,c] = <U[users[u]], I[cand[u,c]]> for a dense [n_u, n_c] int32 candidate matrix."""
+    _need_cuda(U, I)
+    U, I = _f32c(U), _f32c(I)
+    dev = U.device
+    users = _i64c(users, dev)
+    cand = cand.to(device=dev, dtype=torch.int32).contiguous()
+    n_u, n_c = cand.shape
+    score = torch.empty(n_u, n_c, dtype=torch.float32, device=dev)
+    call("spex_score_candidates_f32", ptr(U), ptr(I), U.shape[1], ptr(users), ptr(cand), n_u, n_c,
+         ptr(score), stream_ptr())
+    return score
+
+
+def score_topk_f32(U, I, users, k, mask_rowptr=None, mask_col=None):
+    """Exact fp32 full-ranking top-k (score desc, ties by ascending item id)."""
+    _need_cuda(U, I)
+    U, I = _f32c(U), _f32c(I)
+    dev = U.device
+    users = _i64c(users, dev)
+    B = users.numel()
+    idx = torch.empty(B, k, dtype=torch.int32, device=dev)
+    val = torch.empty(B, k, dtype=torch.float32, device=dev)
+    call("spex_score_topk_f32", ptr(U), ptr(I), U.shape[1], ptr(users), B, I.shape[0],
+         ptr(mask_rowptr), ptr(mask_col), int(k), ptr(idx), ptr(val), stream_ptr())
+    return idx, val
+
+
+def rating_dense(U, I, users, apply_sigmoid: bool = True):
+    """[B, m_items] ratings f(<U[users[b]], I[j]>) — the materialised getUsersRating."""
+    _need_cuda(U, I)
+    U, I = _f32c(U), _f32c(I)
+    dev = U.device
+    users = _i64c(users, dev)
+    B, m = users.numel(), I.shape[0]
+    out = torch.empty(B, m, dtype=torch.float32, device=dev)
+    step = 8 * 65535
+    for s in range(0, B, step):
+        n = min(step, B - s)
+        call("spex_rating_f32", ptr(U), ptr(I), U.shape[1], ptr(users[s:]), n, m,
+             1 if apply_sigmoid else 0, ptr(out[s:]), stream_ptr())
+    return out
+
+
+def pack_bf16(src, rows=None, row_multiple: int = 8, out=None):
+    """fp32 [n, D] (optionally gathered by `rows`) -> bf16 UMMA core-matrix layout, zero padded."""
+    _need_cuda(src)
+    src = _f32c(src)
+    dev = src.device
+    n = src.shape[0] if rows is None else rows.numel()
+    D = src.shape[1]
+    n_pad = (n + row_multiple - 1) // row_multiple * row_multiple
+    if out is None:
+        out = torch.empty(n_pad * D, dtype=torch.bfloat16, device=dev)
+    elif out.numel() < n_pad * D:
+        raise ValueError("pack_bf16: output buffer too small")
+    rows_t = None if rows is None else _i64c(rows, dev)
+    call("spex_pack_bf16", ptr(src), ptr(rows_t), n, n_pad, D, ptr(out), stream_ptr())
+    return out, n_pad
+
+
+def score_topk_bf16(Ub, B, B_pad, Ib, m_items, m_pad, k, user_ids=None, mask_rowptr=None,
+                    mask_col=None, out_idx=None, out_val=None):
+    """tcgen05 bf16 scoring GEMM fused with train-item masking and per-row top-k (D = 64)."""
+    _need_cuda(Ub, Ib)
+    dev = Ub.device
+    if out_idx is None:
+        out_idx = torch.empty(B, k, dtype=torch.int32, device=dev)
+    if out_val is None:
+        out_val = torch.empty(B, k, dtype=torch.float32, device=dev)
+    uid = None if user_ids is None else _i64c(user_ids, dev)
+    call("spex_score_topk_bf16", ptr(Ub), ptr(Ib), B, B_pad, m_items, m_pad, ptr(uid),
+         ptr(mask_rowptr), ptr(mask_col), int(k), ptr(out_idx), ptr(out_val), stream_ptr())
+    return out_idx, out_val
+
+
+def expert_gate(E0, Eout, W):
+    """softmax([E0|Eout].W) convex mix per row (model_expert_s.py:154-161), forward only."""
+    _need_cuda(E0, Eout, W)
+    E0, Eout, W = _f32c(E0), _f32c(Eout), _f32c(W)
+    out = torch.empty_like(E0)
+    call("spex_expert_gate_f32", ptr(E0), ptr(Eout), ptr(W), E0.shape[0], E0.shape[1], ptr(out),
+         stream_ptr())
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step):
+    """In-place dense Adam over one flat fp32 table (torch.optim.Adam arithmetic)."""
+    _need_cuda(p, g, m, v)
+    call("spex_adam_f32", ptr(p), ptr(_f32c(g)), ptr(m), ptr(v), p.numel(), float(lr), float(beta1),
+         float(beta2), float(eps), int(step), stream_ptr())
+
+
+def ngcf_epilogue(ego, side, W1, b1, W2, b2, negative_slope, out=None, norm=None, norm_stride=64):
+    _need_cuda(ego, side)
+    n, D = ego.shape
+    if out is None:
+        out = torch.empty_like(ego)
+    call("spex_ngcf_epilogue_f32", ptr(_f32c(ego)), ptr(_f32c(side)), ptr(_f32c(W1)), ptr(b1),
+         ptr(_f32c(W2)), ptr(b2), n, D, float(negative_slope), ptr(out), ptr(norm), int(norm_stride),
+         stream_ptr())
+    return out
+
+
+def launch_count() -> int:
+    return _capi.launch_count()

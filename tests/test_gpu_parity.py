@@ -1,0 +1,309 @@
+"""GPU parity: the CUDA path (through the C-ABI, via spex_b200.ops / model) against the CPU oracle
+on the same seeded inputs.  Tolerances: 1e-5 relative for fp32 propagation / losses / gradients
+(north_star), exact index agreement modulo score ties for top-k, 1e-2 for bf16 scoring."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import check_topk_against_scores, make_args, oracle_graph, random_graph, rel_err
+from oracle import lightgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _dev_graph(u, i, nur, m, dev, seg_len=1024):
+    from spex_b200 import ops
+    from spex_b200.graph import build_norm_adj
+
+    return ops.DeviceGraph.from_host(build_norm_adj(u, i, nur, m), dev, seg_len=seg_len)
+
+
+@pytest.mark.parametrize("D", [64, 32, 128, 20, 256])
+@pytest.mark.parametrize("seg_len", [1024, 32])
+def test_spmm_matches_sparse_mm(cuda_device, D, seg_len):
+    from spex_b200 import ops
+
+    nu, m = 700, 400
+    u, i = random_graph(nu, m, 9000, 11, hub_items=3, hub_degree=500)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    if seg_len == 32:
+        assert g.n_long > 0
+    torch.manual_seed(0)
+    X = torch.randn(nu + 1 + m, D)
+    ref = torch.sparse.mm(A, X)
+    Y = ops.spmm(g, X.to(cuda_device))
+    assert rel_err(Y, ref) < TOL
+    # empty rows (the padding user) stay exactly zero
+    assert float(Y[nu].abs().max()) == 0.0
+    # fused epilogue: Z = (addend*2 + A.X) * 0.25, Y written too
+    add = torch.randn_like(X)
+    Z = torch.empty_like(X, device=cuda_device)
+    Y2 = torch.empty_like(Z)
+    ops.spmm(g, X.to(cuda_device), Y=Y2, addend=add.to(cuda_device), addend_scale=2.0, Z=Z, z_scale=0.25)
+    assert torch.equal(Y2, Y)
+    assert rel_err(Z, (add * 2 + ref) * 0.25) < TOL
+
+
+@pytest.mark.parametrize("K", [0, 1, 2, 3, 4])
+def test_propagate_mean_and_determinism(cuda_device, K):
+    from spex_b200 import ops
+
+    nu, m, D = 500, 300, 64
+    u, i = random_graph(nu, m, 7000, 5, hub_items=2, hub_degree=400)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len=64)
+    torch.manual_seed(1)
+    E = torch.randn(nu + 1 + m, D) * 0.1
+    ru, ri = O.computer(E[: nu + 1], E[nu + 1:], A, K)
+    out = ops.propagate_mean(E.to(cuda_device), g, K)
+    assert rel_err(out, torch.cat([ru, ri])) < TOL
+    out2 = ops.propagate_mean(E.to(cuda_device), g, K)
+    assert torch.equal(out, out2), "propagation must be bit-reproducible (no atomics)"
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_propagate_backward(cuda_device, dropout):
+    from spex_b200 import ops
+
+    nu, m, D, K = 300, 200, 64, 3
+    u, i = random_graph(nu, m, 4000, 9)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device)
+    torch.manual_seed(2)
+    E = (torch.randn(nu + 1 + m, D) * 0.1).requires_grad_(True)
+    W = torch.randn(nu + 1 + m, D)
+    val = valT = None
+    Aref = A
+    if dropout:
+        rand = torch.rand(A._nnz())
+        Aref = O.dropout_graph(A, 0.6, rand)
+        keep = (rand + 0.6).int().bool()
+        val = g.dropout_values(keep, 0.6)
+        valT = g.transposed_values(val)
+    ru, ri = O.computer(E[: nu + 1], E[nu + 1:], Aref, K)
+    (torch.cat([ru, ri]) * W).sum().backward()
+    Ed = E.detach().to(cuda_device).requires_grad_(True)
+    out = ops.propagate_mean(Ed, g, K, val, valT)
+    assert rel_err(out, torch.cat([ru, ri])) < TOL
+    (out * W.to(cuda_device)).sum().backward()
+    assert rel_err(Ed.grad, E.grad) < TOL
+
+
+def _small_model(cuda_device, **kw):
+    from spex_b200.dataloader import SyntheticDataset
+    from spex_b200.model import LightGCN
+
+    ds = SyntheticDataset(400, 250, 6000, seed=4)
+    torch.manual_seed(2020)
+    model = LightGCN(make_args(**kw), ds)
+    ref_w = (model.embedding_user.weight.detach().clone(), model.embedding_item.weight.detach().clone())
+    A = oracle_graph(ds.trainUser, ds.trainItem, ds.n_users + 1, ds.m_items)
+    return ds, model.to(cuda_device), ref_w, A
+
+
+def test_model_forward_backward_bce(cuda_device):
+    ds, model, (uw, iw), A = _small_model(cuda_device)
+    rng = np.random.default_rng(0)
+    B = 256
+    users = torch.from_numpy(rng.integers(0, ds.n_users, B))
+    users[:40] = users[0]  # heavy duplicates: exercises the segmented scatter
+    items = torch.from_numpy(rng.integers(0, ds.m_items, B))
+    items[100:130] = items[100]
+    labels = torch.from_numpy(rng.integers(0, 2, B))
+    uw.requires_grad_(True)
+    iw.requires_grad_(True)
+    ref = O.bce_forward(uw, iw, A, 3, users, items, labels)
+    ref.backward()
+    model.train()
+    loss = model(users.to(cuda_device), items.to(cuda_device), labels.to(cuda_device), flag=0)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
+    assert rel_err(model.embedding_user.weight.grad, uw.grad) < TOL
+    assert rel_err(model.embedding_item.weight.grad, iw.grad) < TOL
+    # flag=1 returns the logits
+    model.eval()
+    with torch.no_grad():
+        g1 = model(users.to(cuda_device), items.to(cuda_device), None, flag=1)
+        ru, ri = O.computer(uw.detach(), iw.detach(), A, 3)
+    assert rel_err(g1, O.gamma(ru, ri, users, items)) < TOL
+
+
+def test_model_dropout_matches_reference_mask(cuda_device):
+    ds, model, (uw, iw), A = _small_model(cuda_device, dropout=1, keepprob=0.3)
+    users = torch.arange(64) % ds.n_users
+    items = torch.arange(64) % ds.m_items
+    labels = (torch.arange(64) % 2)
+    torch.manual_seed(77)
+    Adrop = O.dropout_graph(A, 0.3)
+    uw.requires_grad_(True)
+    iw.requires_grad_(True)
+    ru, ri = O.computer(uw, iw, Adrop, 3)
+    ref = torch.nn.BCEWithLogitsLoss()(O.gamma(ru, ri, users, items), labels.float())
+    ref.backward()
+    model.train()
+    torch.manual_seed(77)
+    loss = model(users.to(cuda_device), items.to(cuda_device), labels.to(cuda_device), flag=0)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
+    assert rel_err(model.embedding_user.weight.grad, uw.grad) < TOL
+    assert rel_err(model.embedding_item.weight.grad, iw.grad) < TOL
+
+
+def test_model_bpr_loss(cuda_device):
+    ds, model, (uw, iw), A = _small_model(cuda_device)
+    rng = np.random.default_rng(1)
+    B = 512
+    users = torch.from_numpy(rng.integers(0, ds.n_users, B))
+    pos = torch.from_numpy(rng.integers(0, ds.m_items, B))
+    neg = torch.from_numpy(rng.integers(0, ds.m_items, B))
+    uw.requires_grad_(True)
+    iw.requires_grad_(True)
+    rl, rr = O.bpr_loss(uw, iw, A, 3, users, pos, neg)
+    (rl + 1e-2 * rr).backward()
+    model.train()
+    l, r = model.bpr_loss(users.to(cuda_device), pos.to(cuda_device), neg.to(cuda_device))
+    (l + 1e-2 * r).backward()
+    assert abs(float(l) - float(rl)) <= TOL * abs(float(rl))
+    assert abs(float(r) - float(rr)) <= TOL * abs(float(rr))
+    assert rel_err(model.embedding_user.weight.grad, uw.grad) < TOL
+    assert rel_err(model.embedding_item.weight.grad, iw.grad) < TOL
+
+
+def test_adam_matches_torch(cuda_device):
+    from spex_b200 import ops
+
+    torch.manual_seed(3)
+    n = 64 * 1001 + 3
+    p0 = torch.randn(n)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.to(cuda_device)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(n)
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.to(cuda_device), m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+    assert rel_err(p, p_ref) < 1e-6
+
+
+def test_sampled_test_matches_reference_semantics(cuda_device):
+    from spex_b200 import batch_test
+
+    ds, model, (uw, iw), A = _small_model(cuda_device)
+    model.eval()
+    got = batch_test.test(model, ds.testRatings, ds.testNegatives)
+    ru, ri = O.computer(uw, iw, A, 3)
+    want = O.test_sampled(ru, ri, ds.testRatings, ds.testNegatives)
+    # scores agree to 1e-5; rankings can differ only at near-ties, so allow a few users to move
+    n = len(ds.testRatings)
+    assert np.abs(got["recall"] - want["recall"]).max() <= 3.0 / n
+    assert np.abs(got["ndcg"] - want["ndcg"]).max() <= 3.0 / n
+
+
+def test_rating_and_topk_fp32(cuda_device):
+    ds, model, (uw, iw), A = _small_model(cuda_device)
+    model.eval()
+    ru, ri = O.computer(uw, iw, A, 3)
+    users = np.arange(0, ds.n_users, 3)
+    rating = model.getUsersRating(torch.from_numpy(users).to(cuda_device))
+    ref = O.users_rating(ru, ri, torch.from_numpy(users))
+    assert rel_err(rating, ref) < TOL
+    rp, col = ds.getInteractionCSR()
+    masked = [col[rp[u]: rp[u + 1]] for u in users]
+    scores = torch.matmul(ru[users].double(), ri.double().t()).numpy()
+    for k in (1, 20, 128):
+        idx, val = model.rank_topk(users, k=k, precision="fp32")
+        check_topk_against_scores(idx, val, scores, k, masked, atol=1e-6)
+    # determinism + tie-break by ascending id on exact ties (duplicate item rows)
+    from spex_b200 import ops
+
+    I2 = torch.cat([ri[:50], ri[:50]]).to(cuda_device)
+    idx, val = ops.score_topk_f32(ru.to(cuda_device), I2, torch.arange(10), 100)
+    idx = idx.cpu().numpy()
+    for r in range(10):
+        pairs = idx[r].reshape(50, 2)
+        assert (pairs[:, 1] == pairs[:, 0] + 50).all()
+
+
+def test_topk_bf16_tensor_core(cuda_device):
+    from spex_b200 import ops
+
+    torch.manual_seed(5)
+    n_u, m, D = 300, 5000, 64
+    U = (torch.randn(n_u, D) * 0.3).bfloat16().float()
+    I = (torch.randn(m, D) * 0.3).bfloat16().float()
+    users = torch.arange(n_u)
+    rng = np.random.default_rng(2)
+    mu = rng.integers(0, n_u, 6000)
+    mi = rng.integers(0, m, 6000)
+    from spex_b200.graph import build_interaction_csr
+
+    rp, col = build_interaction_csr(mu, mi, n_u, m)
+    masked = [col[rp[u]: rp[u + 1]] for u in range(n_u)]
+    scores = torch.matmul(U.double(), I.double().t()).numpy()
+    Ud, Id = U.to(cuda_device), I.to(cuda_device)
+    Ib, m_pad = ops.pack_bf16(Id, None, 256)
+    Ub, b_pad = ops.pack_bf16(Ud, users.to(cuda_device), 128)
+    rpd = torch.from_numpy(rp).to(cuda_device)
+    cold = torch.from_numpy(col).to(cuda_device)
+    for k in (1, 20, 64):
+        idx, val = ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, k, users.to(cuda_device), rpd, cold)
+        torch.cuda.synchronize()
+        # inputs are exactly representable in bf16, so only the accumulation order differs
+        check_topk_against_scores(idx, val, scores, k, masked, atol=1e-4)
+    # agreement with the exact fp32 scorer on the same inputs (identical modulo near-ties)
+    i32, v32 = ops.score_topk_f32(Ud, Id, users, 20, rpd, cold)
+    i16, v16 = ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, 20, users.to(cuda_device), rpd, cold)
+    assert float((v32 - v16).abs().max()) < 1e-4
+    assert float((i32 == i16).float().mean()) > 0.99
+
+
+def test_model_rank_topk_bf16_vs_fp32(cuda_device):
+    ds, model, (uw, iw), A = _small_model(cuda_device)
+    model.eval()
+    users = np.arange(ds.n_users)
+    i32, v32 = model.rank_topk(users, k=20, precision="fp32")
+    i16, v16 = model.rank_topk(users, k=20, precision="bf16")
+    # bf16 scoring: 1e-2 relative on scores (north_star); sets mostly agree
+    scale = float(v32.abs().max())
+    assert float((v32 - v16).abs().max()) <= 1e-2 * scale
+    same = [(len(set(a.tolist()) & set(b.tolist())) / 20.0) for a, b in zip(i32.cpu().numpy(), i16.cpu().numpy())]
+    assert np.mean(same) > 0.9
+
+
+def test_expert_gate_and_ngcf_epilogue(cuda_device):
+    from spex_b200 import ops
+
+    torch.manual_seed(6)
+    n, D = 1000, 64
+    e0, e1 = torch.randn(n, D), torch.randn(n, D)
+    W = torch.randn(2 * D, 2) * 0.1
+    ref = O.expert_gate(e0, e1, W)
+    got = ops.expert_gate(e0.to(cuda_device), e1.to(cuda_device), W.to(cuda_device))
+    assert rel_err(got, ref) < TOL
+    nu, m = 300, 200
+    u, i = random_graph(nu, m, 4000, 9)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device)
+    ego = torch.randn(nu + 1 + m, D) * 0.1
+    W1, W2 = torch.randn(D, D) * 0.1, torch.randn(D, D) * 0.1
+    b1, b2 = torch.randn(D) * 0.1, torch.randn(D) * 0.1
+    r_out, r_norm = O.ngcf_layer(A, ego, W1, b1, W2, b2, 0.2)
+    side = ops.spmm(g, ego.to(cuda_device))
+    norm = torch.empty(nu + 1 + m, 128, device=cuda_device)
+    out = ops.ngcf_epilogue(ego.to(cuda_device), side, W1.to(cuda_device), b1.to(cuda_device),
+                            W2.to(cuda_device), b2.to(cuda_device), 0.2, norm=norm[:, 64:], norm_stride=128)
+    assert rel_err(out, r_out) < TOL
+    assert rel_err(norm[:, 64:], r_norm) < 1e-5
+
+
+def test_cpu_tensor_is_rejected():
+    from spex_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops.rating_dense(torch.zeros(4, 64), torch.zeros(4, 64), torch.zeros(1, dtype=torch.long))
