@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10M x 5M x 1B workload")
     ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "push"), choices=["nccl", "push"])
-    ap.add_argument("--eval-users", type=int, default=148 * 128 * 2)
+    ap.add_argument("--eval-users", type=int, default=148 * 2 * 128)
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -334,12 +334,12 @@ def run_ours(args):
         gen = torch.Generator(device=dev)
         gen.manual_seed(7 + rank)
         users = torch.randint(0, nu, (n_eval,), device=dev, generator=gen)
-        Ib, m_pad = ops.pack_bf16(I_all, None, 256)
+        Ib, m_pad = ops.pack_bf16(I_all, None, ops.TC_ITEM_MULTIPLE)
         idx = torch.empty(n_eval, TOPK, dtype=torch.int32, device=dev)
         val = torch.empty(n_eval, TOPK, dtype=torch.float32, device=dev)
 
         def eval_step():
-            Ub, b_pad = ops.pack_bf16(U_all, users, 128)
+            Ub, b_pad = ops.pack_bf16(U_all, users, ops.TC_USER_MULTIPLE)
             ops.score_topk_bf16(Ub, n_eval, b_pad, Ib, m, m_pad, TOPK, users, mask_rp, mask_col, idx, val)
 
         eval_step()

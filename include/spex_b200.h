@@ -202,7 +202,7 @@ int spex_pack_bf16(const float* src, const int64_t* rows, int64_t n, int64_t n_p
 /*
  * Full-ranking top-k on the 5th-gen tensor cores (tcgen05.mma kind::f16, bf16 in / fp32 TMEM
  * accumulators), D == 64.  Ub [B_pad,64] / Ib [m_pad,64] are packed tables from spex_pack_bf16
- * (B_pad % 128 == 0, m_pad % 256 == 0).  Scores never reach HBM: the epilogue streams TMEM,
+ * (B_pad % 128 == 0, m_pad % 128 == 0).  Scores never reach HBM: the epilogue streams TMEM,
  * rejects below the per-row running k-th score, applies the training-item mask to survivors
  * and keeps a per-row top-k.  `user_ids` int64 [B] gives the mask row of each scored row
  * (NULL: row b uses mask row b).  Same ordering / output contract as spex_score_topk_f32;

@@ -9,30 +9,45 @@
 //     multiple of 8 rows is therefore ONE contiguous block of global memory and is staged by a
 //     single 1-D bulk async copy (cp.async.bulk -> UBLKCP) that completes on an mbarrier; no
 //     tensor map, no swizzle bookkeeping;
-//   * math: tcgen05.mma.cta_group::1.kind::f16, M=128 users x N=256 items x K=16, four per tile
-//     (D = 64), issued by one thread; fp32 accumulators in TMEM, double buffered (2 x 256 cols);
-//   * epilogue (8 warps): tcgen05.ld 32 columns at a time; a thread owns one user row, keeps the
-//     row's running k-th score in a register and rejects a 32-score batch with one max-tree and one
-//     compare.  Survivors are checked against the user's training items (binary search in the CSR
-//     row of R) and inserted into the row's sorted list in shared memory.  Scores never touch HBM;
-//   * warp roles: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 =
-//     epilogue (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+//   * tile: one CTA owns 128 users (UMMA M=128) and streams the item table in tiles of N=128
+//     through a multi-stage smem ring.  Per tile: 4 tcgen05.mma.cta_group::1.kind::f16 (K = 4 x 16)
+//     issued by one thread; fp32 accumulators in TMEM, double buffered (2 x 128 columns).  A
+//     4-MMA chain has ~400 cycles of fixed issue->commit->wake latency on B200 (measured,
+//     profiles/microbench/mma_lat.cu), far more than its 256 cycles of math, so TWO CTAs are
+//     resident per SM (256 TMEM columns each): four tiles are in flight per SM and the tensor
+//     pipe of one CTA works while the other CTA's chain drains;
+//   * epilogue (4 warps, thread = user row): with K = 64 every accumulator element is read after
+//     only 64 MACs, so the TMEM -> register read (tcgen05.ld, ~170 B/cycle/SM while the MMA pipe
+//     is busy) is the co-bottleneck of the MMA pipe.  Loads are software-pipelined (chunk c+1 in
+//     flight while chunk c is reduced); a 32-score chunk is rejected with a 3-input-max tree
+//     (FMNMX3) and ONE compare against the row's threshold tau;
+//   * survivors (about k*ln(m/k) per row over the whole sweep) must not stall the pipeline: a
+//     survivor is only APPENDED to the row's unsorted candidate buffer in shared memory after a
+//     merge-cursor test against the user's training items (CSR row of R; item ids arrive in
+//     ascending order, so the cursor only moves forward: no binary search, no dependent global
+//     loads).  When a buffer cannot take the next group of survivors the whole warp compacts it:
+//     rank-by-counting over the <= CAP entries (exchanged by warp shuffles), the best k are
+//     rewritten in sorted order and tau becomes the k-th best.
+//     Scores never touch HBM;
+//   * warp roles: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
+//     epilogue (TMEM lane quarter = warp % 4).
 #include "topk.cuh"
 #include <cuda_bf16.h>
-#include <stdlib.h>
 
 namespace spex {
 namespace tc {
 
 constexpr int BM = 128;            // users per CTA  (UMMA M)
-constexpr int BN = 256;            // items per tile (UMMA N)
+constexpr int BN = 128;            // items per tile (UMMA N)
 constexpr int DK = 64;             // embedding dim  (4 x UMMA K)
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * DK * 2;
 constexpr int B_BYTES = BN * DK * 2;
-constexpr int kThreads = 32 * 10;
+constexpr int kThreads = 32 * 6;
 constexpr int kMaxStages = 4;
+constexpr int kTmemCols = 256;     // 2 accumulator buffers x 128 columns; two CTAs share an SM
 constexpr int KMAX_TC = 64;
+constexpr int kGroup = 8;          // appends are capacity-checked every 8 scores
 constexpr uint32_t kSpinLimit = 1u << 26;   // bounded waits: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -101,8 +116,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// tcgen05.ld 32 lanes x 32 columns (one 32-bit word per lane per column) WITHOUT waiting: the
+// registers are only valid after tmem_wait32() on the same array.
+#define SPEX_R32(r)                                                                            \
+  r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], \
+      r[15], r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], \
+      r[28], r[29], r[30], r[31]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -114,38 +134,184 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// wait for every outstanding tcgen05.ld of this thread; the "+r" operands tie the loaded
+// registers to the wait so that no consumer can be scheduled above it.
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                 "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                 "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return d;
+}
+// max of 32 scores in 16 FMNMX3
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+#define F(i) __uint_as_float(r[i])
+  const float a0 = max3(F(0), F(1), F(2)), a1 = max3(F(3), F(4), F(5)), a2 = max3(F(6), F(7), F(8));
+  const float a3 = max3(F(9), F(10), F(11)), a4 = max3(F(12), F(13), F(14));
+  const float a5 = max3(F(15), F(16), F(17)), a6 = max3(F(18), F(19), F(20));
+  const float a7 = max3(F(21), F(22), F(23)), a8 = max3(F(24), F(25), F(26));
+  const float a9 = max3(F(27), F(28), F(29));
+  const float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8);
+  const float b3 = max3(a9, F(30), F(31));
+  return fmaxf(max3(b0, b1, b2), b3);
+#undef F
 }
 
-// Offer one surviving score to a thread-owned sorted list (position-major in shared memory:
-// entry p of this thread lives at lv[p * BM], li[p * BM]).  Rare path, kept out of line; the
-// caller's (tau, n) stay in registers: the new pair is returned packed as (n << 32) | bits(tau).
-__device__ __noinline__ unsigned long long tc_offer(float tau, int n, int64_t mlo, int64_t mhi,
-                                                    float v, int id, int k, int m_items, float* lv,
-                                                    int* li, const int32_t* __restrict__ mask_col) {
-  if (id < m_items && !mask_contains(mask_col, mlo, mhi, id)) {
-    int p = (n < k) ? n : k - 1;
-    while (p > 0 && beats(v, id, lv[(p - 1) * BM], li[(p - 1) * BM])) {
-      lv[p * BM] = lv[(p - 1) * BM];
-      li[p * BM] = li[(p - 1) * BM];
-      --p;
-    }
-    lv[p * BM] = v;
-    li[p * BM] = id;
-    if (n < k) ++n;
-    if (n == k) tau = lv[(k - 1) * BM];
-  }
+// Per-row mask cursor, kept in shared memory because only the rare survivor path touches it.
+// Items are offered to a row in strictly ascending id order (tile, chunk, column) and the row's
+// training items (CSR row of R) are ascending too, so the mask test is a merge: the cursor only
+// moves forward and a row performs at most |train(u)| sequential mask loads over the whole sweep.
+struct MaskCursor {
+  const int32_t* cur[BM];
+  const int32_t* end[BM];
+  int next[BM];                // smallest training item id not yet passed (INT_MAX: none left)
+};
+
+__device__ __forceinline__ unsigned long long pack_state(int n, float tau) {
   return ((unsigned long long)(unsigned)n << 32) | (unsigned long long)__float_as_uint(tau);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// One column of a chunk has at least one survivor in this warp (lanes in `b`).  Called by the
+// whole warp (convergent), out of line.  Each surviving lane runs the mask cursor and appends
+// (v, id) to its row's candidate buffer (row-major in shared memory: entry p of row r at
+// cv[r * CAP + p]); rows whose buffer became full are compacted cooperatively: every lane takes
+// EPL entries into registers, ranks them by counting the entries that beat them (entries travel
+// by warp shuffle; (score desc, id asc) is a strict total order, so ranks are a permutation), the
+// best k are written back in sorted order and the row's threshold becomes its k-th best score.
+// Returns this lane's (n, tau).  `force` compacts the rows in `b` without appending (final pass).
+template <int EPL>
+__device__ __noinline__ unsigned long long tc_column(unsigned b, float v, int id, int n, float tau,
+                                                     int k, int m_items, int lane, int row, float* cv_warp,
+                                                     int* ci_warp, MaskCursor* mc, bool force) {
+  constexpr int CAP = 32 * EPL;
+  unsigned need = b;
+  if (!force) {
+    if (((b >> lane) & 1u) && id < m_items) {   // id >= m_items: zero padding of the last tile
+      int mnext = mc->next[row];
+      if (mnext < id) {
+        const int32_t* c = mc->cur[row];
+        const int32_t* e = mc->end[row];
+        do {
+          ++c;
+          mnext = (c < e) ? __ldg(c) : 0x7fffffff;
+        } while (mnext < id);
+        mc->cur[row] = c;
+        mc->next[row] = mnext;
+      }
+      if (mnext != id) {                        // == id: training item of this user, excluded
+        cv_warp[lane * CAP + n] = v;
+        ci_warp[lane * CAP + n] = id;
+        ++n;
+      }
+    }
+    need = __ballot_sync(kFull, n == CAP);
+  }
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const int ns = __shfl_sync(kFull, n, src);
+    float* cvr = cv_warp + src * CAP;
+    int* cir = ci_warp + src * CAP;
+    float ev[EPL];
+    int ei[EPL], rank[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int p = lane + 32 * e;
+      const bool ok = p < ns;
+      ev[e] = ok ? cvr[p] : -INFINITY;
+      ei[e] = ok ? cir[p] : 0x7fffffff;
+      rank[e] = 0;
+    }
+#pragma unroll
+    for (int e2 = 0; e2 < EPL; ++e2) {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {   // kept rolled: cold code must stay small (i-cache)
+        const float vj = __shfl_sync(kFull, ev[e2], j);
+        const int ij = __shfl_sync(kFull, ei[e2], j);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) rank[e] += beats(vj, ij, ev[e], ei[e]) ? 1 : 0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      if (lane + 32 * e < ns && rank[e] < k) {
+        cvr[rank[e]] = ev[e];
+        cir[rank[e]] = ei[e];
+      }
+    }
+    __syncwarp();
+    const float tau_new = (ns >= k) ? cvr[k - 1] : -INFINITY;
+    if (lane == src) {
+      n = ns < k ? ns : k;
+      tau = tau_new;
+    }
+  }
+  return pack_state(n, tau);
+}
+
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t x;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(x) : : "memory");
+  return __uint_as_float(x);
+}
+
+// reduce one 32-score chunk against the row's threshold.  Fast path: 16 FMNMX3 + one compare +
+// one warp vote.  The kernel is instruction-fetch sensitive (the hot loop must stay resident in
+// the SM's instruction cache while two CTAs and three warp roles share it), so the survivor path
+// is written as LOOPS, not unrolled code: each lane builds a 32-bit mask of its surviving
+// columns, the warp ORs the masks (REDUX) and visits only the columns that have a survivor,
+// re-reading that column from TMEM (the accumulator buffer is still owned by the epilogue).
+template <int EPL>
+__device__ __forceinline__ void consume_chunk(const uint32_t (&r)[32], uint32_t taddr, int item0, int& n,
+                                              float& tau, int k, int m_items, int lane, int row,
+                                              float* cv_warp, int* ci_warp, MaskCursor* mc) {
+  if (__any_sync(kFull, max32(r) > tau)) {
+    unsigned mine = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mine |= (__uint_as_float(r[i]) > tau) ? (1u << i) : 0u;
+    unsigned cols = __reduce_or_sync(kFull, mine);
+#pragma unroll 1
+    while (cols) {
+      const int i = __ffs(cols) - 1;
+      cols &= cols - 1;
+      const float v = tmem_ld1(taddr + i);
+      const unsigned b = __ballot_sync(kFull, v > tau);   // tau may have risen since the mask was built
+      if (b) {
+        const unsigned long long st = tc_column<EPL>(b, v, item0 + i, n, tau, k, m_items, lane, row,
+                                                     cv_warp, ci_warp, mc, false);
+        tau = __uint_as_float((unsigned)(st & 0xffffffffull));
+        n = (int)(st >> 32);
+      }
+    }
+  }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(kThreads, 2)
 score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__ Ib, int64_t B,
                      int m_items, int n_item_tiles, const int64_t* __restrict__ user_ids,
                      const int64_t* __restrict__ mask_rowptr, const int32_t* __restrict__ mask_col,
                      int k, int32_t* __restrict__ out_idx, float* __restrict__ out_val, int stages,
-                     uint32_t lbo, uint32_t sbo) {
+                     long long* __restrict__ trace) {
+  constexpr int CAP = 32 * EPL;
+  // bring-up instrumentation (trace == nullptr in production): CTA 0 records clock64 stamps of
+  // tiles [kTraceT0, kTraceT0 + 64): [t][0..1] MMA thread (buffer free, chain issued),
+  // [t][2..4] epilogue warp 2 (accumulator ready, accumulator drained, tile reduced)
+  constexpr int kTraceT0 = 2000;
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  constexpr uint32_t lbo = 128, sbo = 1024;   // layout written by spex_pack_bf16 (D = 64)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -153,13 +319,14 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ __align__(8) uint64_t bar_a;
   __shared__ uint32_t tmem_slot;
+  __shared__ MaskCursor mc;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + A_BYTES;
-  float* lv = reinterpret_cast<float*>(sB + (size_t)stages * B_BYTES);  // [2][k][BM]
-  int* li = reinterpret_cast<int*>(lv + 2 * k * BM);                    // [2][k][BM]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                             ~(uintptr_t)127);
+  uint8_t* sA = smem;                                                    // [128 users][64] bf16
+  uint8_t* sB = smem + A_BYTES;                                          // stages x [128 items][64]
+  float* cv = reinterpret_cast<float*>(sB + (size_t)stages * B_BYTES);   // [BM][CAP]
+  int* ci = reinterpret_cast<int*>(cv + (size_t)CAP * BM);               // [BM][CAP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t tile_m = blockIdx.x;
@@ -171,7 +338,7 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_tfull[b], 1);
-      mbar_init(&bar_tempty[b], 8);   // one arrive per epilogue warp
+      mbar_init(&bar_tempty[b], 4);   // one arrive per epilogue warp
     }
     mbar_init(&bar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -179,7 +346,7 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&tmem_slot)),
-                 "r"(512u)
+                 "r"((uint32_t)kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -193,12 +360,16 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
     if (lane == 0) {
       mbar_arrive_expect_tx(&bar_a, A_BYTES);
       bulk_g2s(sA, Ub + tile_m * A_BYTES, A_BYTES, &bar_a);
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < n_item_tiles; ++t) {
-        const int s = t % stages;
-        const uint32_t ph = (uint32_t)(t / stages) & 1u;
         mbar_wait(&bar_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&bar_full[s], B_BYTES);
         bulk_g2s(sB + (size_t)s * B_BYTES, Ib + (size_t)t * B_BYTES, B_BYTES, &bar_full[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
@@ -209,105 +380,94 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_addr = smem_u32(sA);
-      const uint32_t kstep = 2 * lbo;  // 16 bf16 along K = two 8-element core matrices
+      constexpr uint32_t kstep = 2 * lbo;  // 16 bf16 along K = two 8-element core matrices
       mbar_wait(&bar_a, 0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < n_item_tiles; ++t) {
-        const int s = t % stages;
-        const uint32_t ph = (uint32_t)(t / stages) & 1u;
         const int buf = t & 1;
         const uint32_t use = (uint32_t)(t >> 1) & 1u;
-        mbar_wait(&bar_tempty[buf], use ^ 1u);
         mbar_wait(&bar_full[s], ph);
+        mbar_wait(&bar_tempty[buf], use ^ 1u);
         tc_fence_after();
+        const bool tr = tracing && t >= kTraceT0 && t < kTraceT0 + 64;
+        if (tr) trace[(t - kTraceT0) * 8 + 0] = clock64();
         const uint32_t b_addr = smem_u32(sB + (size_t)s * B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DK / UMMA_K; ++kk) {
-          tc_mma(tmem_base + (uint32_t)buf * BN, make_desc(a_addr + kk * kstep, lbo, sbo),
+          tc_mma(tmem_base + (uint32_t)(buf * BN), make_desc(a_addr + kk * kstep, lbo, sbo),
                  make_desc(b_addr + kk * kstep, lbo, sbo), idesc, kk > 0 ? 1u : 0u);
         }
         tc_commit(&bar_empty[s]);     // smem stage reusable once these MMAs have read it
         tc_commit(&bar_tfull[buf]);   // accumulator ready for the epilogue
+        if (tr) trace[(t - kTraceT0) * 8 + 1] = clock64();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else {
-    // ===== epilogue: thread owns (row, column half) =====
-    const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int h = (warp - 2) >> 2;      // column half
+    // ===== epilogue: thread owns one user row; warp = TMEM lane quarter =====
+    const int q = warp & 3;
     const int row = q * 32 + lane;
     const int64_t grow = tile_m * BM + row;
-    float* mylv = lv + (size_t)h * k * BM + row;
-    int* myli = li + (size_t)h * k * BM + row;
+    float* cv_warp = cv + q * 32 * CAP;   // + lane * CAP = this thread's row
+    int* ci_warp = ci + q * 32 * CAP;
     int n = 0;
-    int64_t mlo = 0, mhi = 0;
     float tau = (grow < B) ? -INFINITY : INFINITY;   // +inf: padded row, nothing survives
-    if (grow < B && mask_rowptr) {
-      const int64_t uid = user_ids ? user_ids[grow] : grow;
-      mlo = mask_rowptr[uid];
-      mhi = mask_rowptr[uid + 1];
+    {
+      const int32_t* c = mask_col;
+      const int32_t* e = mask_col;
+      int mnext = 0x7fffffff;
+      if (grow < B && mask_rowptr) {
+        const int64_t uid = user_ids ? user_ids[grow] : grow;
+        c = mask_col + mask_rowptr[uid];
+        e = mask_col + mask_rowptr[uid + 1];
+        if (c < e) mnext = __ldg(c);
+      }
+      mc.cur[row] = c;
+      mc.end[row] = e;
+      mc.next[row] = mnext;
     }
+    uint32_t ra[32], rb[32];
     for (int t = 0; t < n_item_tiles; ++t) {
       const int buf = t & 1;
       const uint32_t use = (uint32_t)(t >> 1) & 1u;
       mbar_wait(&bar_tfull[buf], use);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * (BN / 2));
-      const int item0 = t * BN + h * (BN / 2);
+      const bool tr = tracing && warp == 2 && lane == 0 && t >= kTraceT0 && t < kTraceT0 + 64;
+      if (tr) trace[(t - kTraceT0) * 8 + 2] = clock64();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      const int item0 = t * BN;
+      // software pipeline over the four 32-column chunks (two code instances, ra / rb): the
+      // load of chunk c+1 is in flight while chunk c is reduced
+      tmem_ld32_issue(tbase, ra);
+      tmem_wait32(ra);
 #pragma unroll 1
-      for (int c = 0; c < (BN / 2) / 32; ++c) {
-        float v[32];
-        __syncwarp();
-        tmem_ld32(tbase + c * 32, v);
-        float m0 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-        float m1 = fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]));
-        float m2 = fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11]));
-        float m3 = fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]));
-        float m4 = fmaxf(fmaxf(v[16], v[17]), fmaxf(v[18], v[19]));
-        float m5 = fmaxf(fmaxf(v[20], v[21]), fmaxf(v[22], v[23]));
-        float m6 = fmaxf(fmaxf(v[24], v[25]), fmaxf(v[26], v[27]));
-        float m7 = fmaxf(fmaxf(v[28], v[29]), fmaxf(v[30], v[31]));
-        const float mx = fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
-        if (mx > tau) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (v[i] > tau) {
-              const unsigned long long r = tc_offer(tau, n, mlo, mhi, v[i], item0 + c * 32 + i, k,
-                                                    m_items, mylv, myli, mask_col);
-              tau = __uint_as_float((unsigned)(r & 0xffffffffull));
-              n = (int)(r >> 32);
-            }
-          }
-        }
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t tb = tbase + 64 * h;
+        tmem_ld32_issue(tb + 32, rb);
+        consume_chunk<EPL>(ra, tb, item0 + 64 * h, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
+        tmem_wait32(rb);
+        if (h == 0) tmem_ld32_issue(tbase + 64, ra);
+        consume_chunk<EPL>(rb, tb + 32, item0 + 64 * h + 32, n, tau, k, m_items, lane, row, cv_warp, ci_warp,
+                           &mc);
+        if (h == 0) tmem_wait32(ra);
       }
+      // every column of this accumulator has been reduced: hand the TMEM buffer back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+      if (tr) trace[(t - kTraceT0) * 8 + 3] = clock64();
     }
-    // publish list lengths, then the h == 0 thread of each row merges the two halves
-    __shared__ int nlist[2][BM];
-    nlist[h][row] = n;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (h == 0 && grow < B) {
-      const float* av = lv + row;
-      const int* ai = li + row;
-      const float* bv = lv + (size_t)k * BM + row;
-      const int* bi = li + (size_t)k * BM + row;
-      const int na = nlist[0][row], nb = nlist[1][row];
-      int pa = 0, pb = 0;
+    // final compaction of every row (sorted best-first), then each thread writes its own row
+    n = (int)(tc_column<EPL>(kFull, 0.f, 0, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc, true) >> 32);
+    if (grow < B) {
       for (int p = 0; p < k; ++p) {
-        int id = -1;
-        float val = -INFINITY;
-        const bool ha = pa < na, hb = pb < nb;
-        if (ha && (!hb || beats(av[pa * BM], ai[pa * BM], bv[pb * BM], bi[pb * BM]))) {
-          val = av[pa * BM];
-          id = ai[pa * BM];
-          ++pa;
-        } else if (hb) {
-          val = bv[pb * BM];
-          id = bi[pb * BM];
-          ++pb;
-        }
-        out_idx[grow * k + p] = id;
-        out_val[grow * k + p] = val;
+        const bool ok = p < n;
+        out_idx[grow * k + p] = ok ? ci_warp[lane * CAP + p] : -1;
+        out_val[grow * k + p] = ok ? cv_warp[lane * CAP + p] : -INFINITY;
       }
     }
   }
@@ -315,7 +475,8 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)kTmemCols)
                  : "memory");
   }
 }
@@ -372,8 +533,38 @@ extern "C" int spex_pack_bf16(const float* src, const int64_t* rows, int64_t n, 
   return check_last();
 }
 
-static size_t tc_smem_bytes(int k, int stages) {
-  return 1024 + (size_t)tc::A_BYTES + (size_t)stages * tc::B_BYTES + (size_t)2 * k * tc::BM * 8;
+static long long* g_tc_trace = nullptr;
+// bring-up only (not part of the declared ABI): device buffer of 64*8 int64 clock stamps
+extern "C" void spex_debug_tc_trace(void* dev_buf) { g_tc_trace = (long long*)dev_buf; }
+
+static size_t tc_smem_bytes(int cap, int stages) {
+  return 128 + (size_t)tc::A_BYTES + (size_t)stages * tc::B_BYTES + (size_t)cap * tc::BM * 8;
+}
+
+template <int EPL>
+static int tc_launch(const void* Ub, const void* Ib, int64_t B, int64_t B_pad, int64_t m_items,
+                     int64_t m_pad, const int64_t* user_ids, const int64_t* mask_rowptr,
+                     const int32_t* mask_col, int32_t k, int32_t* out_idx, float* out_val,
+                     cudaStream_t st) {
+  // two CTAs per SM need <= ~113 KB each (228 KB per SM, 1 KB reserved per CTA, static smem)
+  int stages = tc::kMaxStages;
+  while (stages > 2 && tc_smem_bytes(32 * EPL, stages) + 2800 > 115712) --stages;
+  const size_t smem = tc_smem_bytes(32 * EPL, stages);
+  SPEX_RETURN_IF(smem > 226 * 1024, SPEX_E_TOOBIG);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc::score_topk_tc_kernel<EPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int64_t grid = B_pad / tc::BM;
+  SPEX_RETURN_IF(grid > 0x7fffffffLL, SPEX_E_TOOBIG);
+  tc::score_topk_tc_kernel<EPL><<<(unsigned)grid, tc::kThreads, smem, st>>>(
+      (const uint8_t*)Ub, (const uint8_t*)Ib, B, (int)m_items, (int)(m_pad / tc::BN), user_ids,
+      mask_rowptr, mask_col, k, out_idx, out_val, stages, g_tc_trace);
+  count_launch();
+  return check_last();
 }
 
 extern "C" int spex_score_topk_bf16(const void* Ub, const void* Ib, int64_t B, int64_t B_pad,
@@ -388,27 +579,11 @@ extern "C" int spex_score_topk_bf16(const void* Ub, const void* Ib, int64_t B, i
   SPEX_RETURN_IF(k < 1 || k > tc::KMAX_TC || m_pad > 0x7fffffffLL, SPEX_E_TOOBIG);
   SPEX_RETURN_IF(!aligned16(Ub) || !aligned16(Ib), SPEX_E_ALIGN);
   if (B == 0) return 0;
-  int stages = tc::kMaxStages;
-  while (stages > 2 && tc_smem_bytes(k, stages) > 220 * 1024) --stages;
-  const size_t smem = tc_smem_bytes(k, stages);
-  SPEX_RETURN_IF(smem > 227 * 1024, SPEX_E_TOOBIG);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc::score_topk_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  // K-major no-swizzle canonical layout as packed by spex_pack_bf16 (D = 64):
-  //   LBO = 128 B between core matrices adjacent in K, SBO = 1024 B between 8-row groups.
-  uint32_t lbo = 128, sbo = 1024;
-  if (const char* e = getenv("SPEX_TC_LBO")) lbo = (uint32_t)atoi(e);   // bring-up overrides only
-  if (const char* e = getenv("SPEX_TC_SBO")) sbo = (uint32_t)atoi(e);
-  const int64_t grid = B_pad / tc::BM;
-  SPEX_RETURN_IF(grid > 0x7fffffffLL, SPEX_E_TOOBIG);
-  tc::score_topk_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, (cudaStream_t)stream>>>(
-      (const uint8_t*)Ub, (const uint8_t*)Ib, B, (int)m_items, (int)(m_pad / tc::BN), user_ids,
-      mask_rowptr, mask_col, k, out_idx, out_val, stages, lbo, sbo);
-  count_launch();
-  return check_last();
+  cudaStream_t st = (cudaStream_t)stream;
+  // candidate buffer capacity CAP = 32*EPL must hold k kept entries + one group of appends
+  if (k <= 32 - tc::kGroup)
+    return tc_launch<1>(Ub, Ib, B, B_pad, m_items, m_pad, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
+  if (k <= 64 - tc::kGroup)
+    return tc_launch<2>(Ub, Ib, B, B_pad, m_items, m_pad, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
+  return tc_launch<3>(Ub, Ib, B, B_pad, m_items, m_pad, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
 }

@@ -238,7 +238,7 @@ class LightGCN(BasicModel):
         if self.latent_dim != 64:
             raise RuntimeError("the tcgen05 scorer is built for recdim == 64")
         if self._item_pack is None or self.training:
-            Ib, m_pad = ops.pack_bf16(all_items, None, 256)
+            Ib, m_pad = ops.pack_bf16(all_items, None, ops.TC_ITEM_MULTIPLE)
             self._item_pack = (Ib, m_pad)
         Ib, m_pad = self._item_pack
         B = users.numel()
@@ -246,7 +246,7 @@ class LightGCN(BasicModel):
         val = torch.empty(B, k, dtype=torch.float32, device=dev)
         for s in range(0, B, user_block):
             ub = users[s: s + user_block]
-            Ub, b_pad = ops.pack_bf16(all_users, ub, 128)
+            Ub, b_pad = ops.pack_bf16(all_users, ub, ops.TC_USER_MULTIPLE)
             ops.score_topk_bf16(Ub, ub.numel(), b_pad, Ib, self.num_items, m_pad, k, ub, mrp, mcol,
                                 idx[s: s + ub.numel()], val[s: s + ub.numel()])
         return idx, val

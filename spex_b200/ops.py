@@ -378,6 +378,10 @@ def rating_dense(U, I, users, apply_sigmoid: bool = True):
     return out
 
 
+TC_USER_MULTIPLE = 128   # users per CTA of the tcgen05 scorer (UMMA M)
+TC_ITEM_MULTIPLE = 128   # items per tile (UMMA N)
+
+
 def pack_bf16(src, rows=None, row_multiple: int = 8, out=None):
     """fp32 [n, D] (optionally gathered by `rows`) -> bf16 UMMA core-matrix layout, zero padded."""
     _need_cuda(src)

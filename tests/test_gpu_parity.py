@@ -247,8 +247,8 @@ def test_topk_bf16_tensor_core(cuda_device):
     masked = [col[rp[u]: rp[u + 1]] for u in range(n_u)]
     scores = torch.matmul(U.double(), I.double().t()).numpy()
     Ud, Id = U.to(cuda_device), I.to(cuda_device)
-    Ib, m_pad = ops.pack_bf16(Id, None, 256)
-    Ub, b_pad = ops.pack_bf16(Ud, users.to(cuda_device), 128)
+    Ib, m_pad = ops.pack_bf16(Id, None, ops.TC_ITEM_MULTIPLE)
+    Ub, b_pad = ops.pack_bf16(Ud, users.to(cuda_device), ops.TC_USER_MULTIPLE)
     rpd = torch.from_numpy(rp).to(cuda_device)
     cold = torch.from_numpy(col).to(cuda_device)
     for k in (1, 20, 64):
