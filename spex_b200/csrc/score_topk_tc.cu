@@ -33,6 +33,7 @@
 //     epilogue (TMEM lane quarter = warp % 4).
 #include "topk.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace spex {
 namespace tc {
@@ -430,7 +431,7 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
       mc.end[row] = e;
       mc.next[row] = mnext;
     }
-    uint32_t ra[32], rb[32];
+    uint32_t ra[32], rb[32], rc[32];
     for (int t = 0; t < n_item_tiles; ++t) {
       const int buf = t & 1;
       const uint32_t use = (uint32_t)(t >> 1) & 1u;
@@ -440,21 +441,21 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
       if (tr) trace[(t - kTraceT0) * 8 + 2] = clock64();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
       const int item0 = t * BN;
-      // software pipeline over the four 32-column chunks (two code instances, ra / rb): the
-      // load of chunk c+1 is in flight while chunk c is reduced
+      // software pipeline over the four 32-column chunks with three register buffers: two
+      // tcgen05.ld are in flight while a chunk is reduced (TMEM read latency is ~190 cycles per
+      // 4 KB while the MMA pipe is busy, so the read rate scales with the loads in flight)
       tmem_ld32_issue(tbase, ra);
+      tmem_ld32_issue(tbase + 32, rb);
       tmem_wait32(ra);
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t tb = tbase + 64 * h;
-        tmem_ld32_issue(tb + 32, rb);
-        consume_chunk<EPL>(ra, tb, item0 + 64 * h, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
-        tmem_wait32(rb);
-        if (h == 0) tmem_ld32_issue(tbase + 64, ra);
-        consume_chunk<EPL>(rb, tb + 32, item0 + 64 * h + 32, n, tau, k, m_items, lane, row, cv_warp, ci_warp,
-                           &mc);
-        if (h == 0) tmem_wait32(ra);
-      }
+      tmem_wait32(rb);
+      tmem_ld32_issue(tbase + 64, rc);
+      consume_chunk<EPL>(ra, tbase, item0, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
+      tmem_ld32_issue(tbase + 96, ra);
+      consume_chunk<EPL>(rb, tbase + 32, item0 + 32, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
+      tmem_wait32(rc);
+      tmem_wait32(ra);
+      consume_chunk<EPL>(rc, tbase + 64, item0 + 64, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
+      consume_chunk<EPL>(ra, tbase + 96, item0 + 96, n, tau, k, m_items, lane, row, cv_warp, ci_warp, &mc);
       // every column of this accumulator has been reduced: hand the TMEM buffer back
       tc_fence_before();
       __syncwarp();
@@ -549,6 +550,7 @@ static int tc_launch(const void* Ub, const void* Ib, int64_t B, int64_t B_pad, i
   // two CTAs per SM need <= ~113 KB each (228 KB per SM, 1 KB reserved per CTA, static smem)
   int stages = tc::kMaxStages;
   while (stages > 2 && tc_smem_bytes(32 * EPL, stages) + 2800 > 115712) --stages;
+  if (const char* e = getenv("SPEX_TC_STAGES")) stages = atoi(e);   // bring-up experiment
   const size_t smem = tc_smem_bytes(32 * EPL, stages);
   SPEX_RETURN_IF(smem > 226 * 1024, SPEX_E_TOOBIG);
   static bool configured = false;
