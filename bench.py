@@ -202,7 +202,7 @@ def run_ours(args):
     from spex_b200 import ops, synthetic
     from spex_b200 import _capi
     from spex_b200.dist import PartitionedPropagator
-    from spex_b200.graph import partition_rows_by_nnz
+    from spex_b200.graph import partition_rows_by_nnz, rebalance_bounds
 
     _capi.device_check()
     hbm_peak, tc_burst, tc_sust, peak_kind = peaks()
@@ -240,13 +240,39 @@ def run_ours(args):
         local_nnz = nnz
         local_rows = N
         prop = None
+        balance_log = None
     else:
         rp_host = g.rowptr.cpu().numpy()
         bounds = partition_rows_by_nnz(rp_host, world)
-        r0, r1 = bounds[rank], bounds[rank + 1]
-        lo, hi = int(rp_host[r0]), int(rp_host[r1])
-        lg = ops.DeviceGraph((g.rowptr[r0: r1 + 1] - lo).contiguous(), g.col[lo:hi].clone(),
-                             g.val[lo:hi].clone(), N, None, g.seg_len, row_offset=r0)
+        # set-up (untimed): equalise the MEASURED local SpMM time of the ranks.  Blocks of user rows
+        # (popular item rows hit L2) and of item rows (random user rows do not) cost differently
+        # per edge, so a pure nnz balance leaves the item-row ranks as stragglers.
+        balance_log = []
+        for it in range(3):
+            r0, r1 = bounds[rank], bounds[rank + 1]
+            lo, hi = int(rp_host[r0]), int(rp_host[r1])
+            lg = ops.DeviceGraph((g.rowptr[r0: r1 + 1] - lo).contiguous(), g.col[lo:hi], g.val[lo:hi], N,
+                                 None, g.seg_len, row_offset=r0)
+            if it == 2:
+                break
+            y = torch.empty(r1 - r0, D, dtype=torch.float32, device=dev)
+            for _ in range(2):
+                ops.spmm(lg, table, Y=y)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ops.spmm(lg, table, Y=y)
+            e1.record()
+            torch.cuda.synchronize()
+            tl = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(tl) for _ in range(world)]
+            dist.all_gather(allt, tl)
+            times = [float(x.item()) for x in allt]
+            balance_log.append([round(x, 3) for x in times])
+            bounds = rebalance_bounds(rp_host, bounds, times)
+            del y, lg
+        lg = ops.DeviceGraph(lg.rowptr, lg.col.clone(), lg.val.clone(), N, None, g.seg_len, row_offset=r0)
         E0_local = table[r0:r1].clone()
         del g, table
         torch.cuda.empty_cache()
@@ -386,7 +412,8 @@ def run_ours(args):
                        "edges_definition": "nnz(A) = 2*|R| per layer", "l2": "inputs larger than L2 (no flush needed)"
                        if nnz * 8 > 200e6 else "inputs smaller than L2: timing is L2-warm",
                        "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" if world > 1 else ""),
-                       "graph_build_s": round(t_gen, 2)},
+                       "graph_build_s": round(t_gen, 2),
+                       "balance_ms_per_rank": balance_log if world > 1 else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
         }

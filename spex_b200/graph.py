@@ -208,6 +208,35 @@ def partition_rows_by_nnz(rowptr: np.ndarray, parts: int, row_cost: float = 2.0)
     return bounds
 
 
+def rebalance_bounds(rowptr: np.ndarray, bounds: List[int], times, row_cost: float = 2.0) -> List[int]:
+    """Re-split the rows so that every part takes the same MEASURED time.
+
+    `times[p]` is the time part p needed for its current block.  The cost of a row is modelled as
+    (its nnz + row_cost) times the cost density of the block it currently lives in (user rows that
+    gather popular items hit L2, item rows that gather random users do not, so the density differs
+    between blocks).  Returns new boundaries with equal modelled cost per part.
+    """
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    n = rowptr.size - 1
+    parts = len(bounds) - 1
+    work = (rowptr + (row_cost * np.arange(n + 1)).astype(np.int64)).astype(np.float64)
+    cost = np.zeros(n + 1, dtype=np.float64)  # cumulative modelled cost at each row boundary
+    acc = 0.0
+    for p in range(parts):
+        a, b = int(bounds[p]), int(bounds[p + 1])
+        w = work[b] - work[a]
+        dens = (float(times[p]) / w) if w > 0 else 0.0
+        cost[a: b + 1] = acc + (work[a: b + 1] - work[a]) * dens
+        acc = cost[b]
+    new = [0]
+    for p in range(1, parts):
+        target = acc * p / parts
+        r = int(np.searchsorted(cost, target, side="left"))
+        new.append(min(max(r, new[-1]), n))
+    new.append(n)
+    return new
+
+
 def fold_rows(n: int, folds: int) -> List[Tuple[int, int]]:
     """The reference's serial row folds (dataloader.py:167-177): equal row counts, last takes the rest."""
     fold_len = n // folds

@@ -185,3 +185,28 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_rebalance_equalises_modelled_cost():
+    from spex_b200.graph import build_norm_adj, partition_rows_by_nnz, rebalance_bounds
+
+    u, i = random_graph(3000, 400, 60000, 5)
+    g = build_norm_adj(u, i, 3001, 400)
+    b = partition_rows_by_nnz(g.rowptr, 4)
+    # pretend the last two parts (item rows) are 1.5x slower per unit of work
+    work = lambda a, c: (g.rowptr[c] - g.rowptr[a]) + 2 * (c - a)
+    dens = [1.0, 1.0, 1.5, 1.5]
+    times = [work(b[p], b[p + 1]) * dens[p] for p in range(4)]
+    nb = rebalance_bounds(g.rowptr, b, times)
+    assert nb[0] == 0 and nb[-1] == g.n_rows and all(nb[k] <= nb[k + 1] for k in range(4))
+    # modelled cost of the new parts (same densities by old block) is equal within a few rows
+    def cost(a, c):
+        tot = 0.0
+        for p in range(4):
+            lo, hi = max(a, b[p]), min(c, b[p + 1])
+            if hi > lo:
+                tot += work(lo, hi) * dens[p]
+        return tot
+    costs = [cost(nb[p], nb[p + 1]) for p in range(4)]
+    assert max(costs) - min(costs) <= 0.02 * sum(costs) / 4 + 3 * g.degrees().max()
+    assert max(costs) < max(times)
