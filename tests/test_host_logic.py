@@ -210,3 +210,18 @@ def test_rebalance_equalises_modelled_cost():
     costs = [cost(nb[p], nb[p + 1]) for p in range(4)]
     assert max(costs) - min(costs) <= 0.02 * sum(costs) / 4 + 3 * g.degrees().max()
     assert max(costs) < max(times)
+
+
+def test_epoch_batches_follow_dataloader_shuffle():
+    from torch.utils.data import DataLoader, TensorDataset
+
+    from spex_b200.main_rec import epoch_batches
+
+    ds = TensorDataset(torch.arange(1000))
+    torch.manual_seed(5)
+    ref = [b[0] for b in DataLoader(ds, batch_size=256, shuffle=True)]
+    ref2 = [b[0] for b in DataLoader(ds, batch_size=256, shuffle=True)]
+    torch.manual_seed(5)
+    mine, mine2 = epoch_batches(1000, 256), epoch_batches(1000, 256)
+    assert all(torch.equal(a, b) for a, b in zip(ref, mine)) and len(ref) == len(mine)
+    assert all(torch.equal(a, b) for a, b in zip(ref2, mine2))
