@@ -43,20 +43,28 @@ int spex_device_check(int* sm_count, int* cc_major, int* cc_minor);
 int64_t spex_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
- * Long-row plan.  Rows with more than `seg_len` non-zeros are cut into segments of seg_len
- * edges; each segment is reduced by one warp into a partial row and the partials of a row are
- * summed in segment order (deterministic two-pass — no atomics).  The plan is built once per
- * graph by the host (spex_b200/graph.py: plan_long_rows) and passed to every SpMM as a HOST
- * struct holding device pointers; NULL (or n_long == 0) means "no long rows".
+ * Long-row plan.  Rows with more than `seg_len` non-zeros are cut into segments; each segment is
+ * reduced by one warp into a partial row and the partials of a row are summed in a fixed order
+ * (deterministic two-pass — no atomics).  Two segmentations:
+ *   fixed-length   (seg_start == NULL): segments of seg_len consecutive edges; segment j of long
+ *                  row r is partial row long_segptr[r] + j;
+ *   column-blocked (seg_start != NULL): segments are (row, column block) pairs listed in
+ *                  BLOCK-MAJOR order so that concurrently running warps gather from one L2-sized
+ *                  window of the table; row_seg lists each row's segments in column order.
+ * The plan is built once per graph by the host (spex_b200/ops.py: DeviceGraph) and passed to every
+ * SpMM as a HOST struct holding device pointers; NULL (or n_long == 0) means "no long rows".
  * ------------------------------------------------------------------------------------------ */
 typedef struct spex_long_plan {
-  int32_t seg_len;            /* segment length in edges (>= 32)                              */
-  int32_t n_long;             /* number of rows with degree > seg_len                         */
-  int32_t n_seg;              /* total number of segments = long_segptr[n_long]               */
+  int32_t seg_len;            /* rows with degree > seg_len take the long-row path (>= 32)    */
+  int32_t n_long;             /* number of such rows                                          */
+  int32_t n_seg;              /* total number of segments                                     */
   int32_t reserved;
   const int32_t* long_rows;   /* int32 [n_long]    row ids, ascending                         */
-  const int32_t* long_segptr; /* int32 [n_long+1]  exclusive scan of ceil(deg/seg_len)        */
+  const int32_t* long_segptr; /* int32 [n_long+1]  exclusive scan of segments per long row    */
   float* partial;             /* fp32  [n_seg, D]  workspace                                  */
+  const int64_t* seg_start;   /* int64 [n_seg]  first edge of each segment (NULL: fixed-length) */
+  const int32_t* seg_count;   /* int32 [n_seg]  edges in each segment                         */
+  const int32_t* row_seg;     /* int32 [n_seg]  segment ids grouped by long row, column order */
 } spex_long_plan;
 
 /*

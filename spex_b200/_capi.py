@@ -29,6 +29,9 @@ class LongPlan(C.Structure):
         ("long_rows", _p),
         ("long_segptr", _p),
         ("partial", _p),
+        ("seg_start", _p),
+        ("seg_count", _p),
+        ("row_seg", _p),
     ]
 
 

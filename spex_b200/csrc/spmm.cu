@@ -31,12 +31,16 @@ struct RowShape {
 };
 
 // Sum over edges e in [start,end) of val[e] * X[col[e], :], returned in every lane for the
-// float4 slot `lane % LPR`.  kIdentity: col[e] = e, val[e] = 1 (used to sum partial rows).
-template <int D, int U, bool kIdentity>
+// float4 slot `lane % LPR`.  kMode 0: CSR edges; 1: col[e] = e, val[e] = 1 (sum of consecutive
+// partial rows); 2: col[e] from the list, val[e] = 1 (sum of listed partial rows).
+// kFirst: the first 32 edges' (col, val) were loaded by the caller (c0, v0) while the previous row
+// was being reduced (software prefetch in the persistent kernels).
+template <int D, int U, int kMode, bool kFirst = false>
 __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict__ col,
                                                       const float* __restrict__ val,
                                                       const float* __restrict__ X, int64_t start,
-                                                      int64_t end, int lane) {
+                                                      int64_t end, int lane, int c0 = 0,
+                                                      float v0 = 0.f) {
   constexpr int LPR = RowShape<D>::LPR, G = RowShape<D>::G;
   const int grp = lane / LPR, sub = lane % LPR;
   const float* Xs = X + sub * 4;
@@ -45,9 +49,15 @@ __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict_
     const int64_t e = base + lane;
     int c = 0;
     float v = 0.f;
-    if (e < end) {
-      if (kIdentity) {
+    if (kFirst && base == start) {
+      c = c0;
+      v = v0;
+    } else if (e < end) {
+      if (kMode == 1) {
         c = (int)e;
+        v = 1.f;
+      } else if (kMode == 2) {
+        c = ld_stream_s32(col + e);
         v = 1.f;
       } else {
         c = ld_stream_s32(col + e);
@@ -129,7 +139,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
   if (row >= n_rows) return;
   const int64_t start = rowptr[row], end = rowptr[row + 1];
   if (skip_longer_than > 0 && end - start > skip_longer_than) return;  // long-row path
-  const float4 acc = warp_row_accumulate<D, U, false>(col, val, X, start, end, lane);
+  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, end, lane);
   row_epilogue<D>(ep, acc, row, lane);
 }
 
@@ -156,7 +166,7 @@ spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restri
   const int64_t rs = rowptr[row], re = rowptr[row + 1];
   const int64_t start = rs + (int64_t)k * seg_len;
   const int64_t end = (start + seg_len < re) ? start + seg_len : re;
-  const float4 acc = warp_row_accumulate<D, U, false>(col, val, X, start, end, lane);
+  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, end, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -169,8 +179,42 @@ spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (r >= n_long) return;
-  const float4 acc = warp_row_accumulate<D, U, true>(nullptr, nullptr, partial, long_segptr[r],
-                                                     long_segptr[r + 1], lane);
+  const float4 acc = warp_row_accumulate<D, U, 1>(nullptr, nullptr, partial, long_segptr[r],
+                                                  long_segptr[r + 1], lane);
+  row_epilogue<D>(ep, acc, (int64_t)long_rows[r], lane);
+}
+
+// ---- column-blocked long rows ----------------------------------------------------------------
+// Long rows (hub items: thousands of edges, columns spread over the whole table) are cut at fixed
+// COLUMN-block boundaries instead of fixed edge counts, and the segments are launched in
+// block-major order: at any moment the resident warps gather from one ~32 MB window of the
+// table, which the 126 MB L2 keeps resident, so each table row of the window comes from HBM once
+// instead of once per edge.  warp per (row, column block) segment -> partial[seg, :]
+template <int D, int U>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
+                     const float* __restrict__ X, const int64_t* __restrict__ seg_start,
+                     const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial) {
+  constexpr int LPR = RowShape<D>::LPR;
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int64_t start = seg_start[seg];
+  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, start + seg_count[seg], lane);
+  if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
+}
+
+// warp per long row: sum its partial rows in column-block order (fixed order), then the epilogue
+template <int D, int U>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+spmm_long_fix_list_kernel(const int32_t* __restrict__ long_rows,
+                          const int32_t* __restrict__ long_segptr, const int32_t* __restrict__ row_seg,
+                          int32_t n_long, const float* __restrict__ partial, Epilogue ep) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  if (r >= n_long) return;
+  const float4 acc = warp_row_accumulate<D, U, 2>(row_seg, nullptr, partial, long_segptr[r],
+                                                  long_segptr[r + 1], lane);
   row_epilogue<D>(ep, acc, (int64_t)long_rows[r], lane);
 }
 
@@ -240,12 +284,19 @@ static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* va
   count_launch();
   if (has_long) {
     const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
-    spmm_long_seg_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
-        plan->seg_len, plan->partial);
     const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;
-    spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
-        plan->long_rows, plan->long_segptr, plan->n_long, plan->partial, ep);
+    if (plan->seg_start) {   // column-blocked segmentation (block-major launch order)
+      spmm_seg_list_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
+          col, val, X, plan->seg_start, plan->seg_count, plan->n_seg, plan->partial);
+      spmm_long_fix_list_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
+          plan->long_rows, plan->long_segptr, plan->row_seg, plan->n_long, plan->partial, ep);
+    } else {                 // fixed-length segmentation
+      spmm_long_seg_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
+          rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
+          plan->seg_len, plan->partial);
+      spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
+          plan->long_rows, plan->long_segptr, plan->n_long, plan->partial, ep);
+    }
     count_launch(2);
   }
   return check_last();
@@ -263,6 +314,7 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
     SPEX_RETURN_IF(plan->seg_len < 32 || !plan->long_rows || !plan->long_segptr ||
                        !plan->partial || plan->n_seg < plan->n_long,
                    SPEX_E_BADARG);
+    SPEX_RETURN_IF(plan->seg_start && (!plan->seg_count || !plan->row_seg), SPEX_E_BADARG);
     SPEX_RETURN_IF(!aligned16(plan->partial), SPEX_E_ALIGN);
   }
   if (n_rows == 0) return 0;

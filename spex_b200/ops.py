@@ -97,24 +97,96 @@ class DeviceGraph:
         val = A.values().to(dev).to(torch.float32)
         return cls(rowptr, col, val, n_cols, None, seg_len)
 
+    # -- long-row plan --------------------------------------------------------------------------
+    L2_WINDOW_BYTES = 16 << 20   # table bytes per column block: a window the 126 MB L2 keeps
+    MIN_CB_COLS = 1024
+    HUB_EDGES_PER_BLOCK = 64     # average edges per (row, column block) that make blocking pay
+
     def _build_plan(self, D: int):
-        rp = self.rowptr.cpu().numpy() if self.n_rows < (1 << 26) else None
-        if rp is None:
-            deg = (self.rowptr[1:] - self.rowptr[:-1])
-            long_rows_t = torch.nonzero(deg > self.seg_len).flatten()
-            nseg = (deg[long_rows_t] + self.seg_len - 1) // self.seg_len
-            segptr = torch.zeros(long_rows_t.numel() + 1, dtype=torch.int64, device=self.device)
-            torch.cumsum(nseg, 0, out=segptr[1:])
-            long_rows = long_rows_t.to(torch.int32)
-            segptr = segptr.to(torch.int32)
-        else:
-            lr, sp = plan_long_rows(rp, self.seg_len)
-            long_rows = torch.from_numpy(lr).to(self.device)
-            segptr = torch.from_numpy(sp).to(self.device)
-        self.long_rows, self.long_segptr = long_rows, segptr
+        dev = self.device
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        long_rows = torch.nonzero(deg > self.seg_len).flatten()
         self.n_long = int(long_rows.numel())
-        self.n_seg = int(segptr[-1].item()) if self.n_long else 0
+        self.long_rows = long_rows.to(torch.int32)
+        self.seg_start = self.seg_count = self.row_seg = None
         self._plan_D = 0
+        if self.n_long == 0:
+            self.long_segptr = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.n_seg = 0
+            return
+        table_bytes = self.n_cols * D * 4
+        if table_bytes <= 4 * self.L2_WINDOW_BYTES:
+            # fixed-length segments (the whole table fits in L2 anyway)
+            nseg = (deg[long_rows] + self.seg_len - 1) // self.seg_len
+            segptr = torch.zeros(self.n_long + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(nseg, 0, out=segptr[1:])
+            self.long_segptr = segptr.to(torch.int32)
+            self.n_seg = int(segptr[-1].item())
+            return
+        # Explicit segment list (include/spex_b200.h: spex_long_plan, column-blocked form):
+        #   hub rows  (>= HUB_EDGES_PER_BLOCK edges per column block on average) are cut at column-
+        #             block boundaries and listed BLOCK-MAJOR: concurrently running warps gather
+        #             from one ~32 MB window of the table, which L2 keeps resident.  Measured
+        #             (profiles/microbench/l2_window.py): 12.7 TB/s for 128-edge rows in a 32 MB
+        #             window vs 6.8 TB/s over the whole table - but only 6.7 TB/s for 16-edge rows,
+        #             so rows too short to fill their blocks stay on
+        #   mid rows  fixed-length segments of seg_len consecutive edges.
+        import os as _os
+        win = int(_os.environ.get("SPEX_L2_WINDOW_MB", 0)) << 20 or self.L2_WINDOW_BYTES
+        epb = int(_os.environ.get("SPEX_HUB_EPB", 0)) or self.HUB_EDGES_PER_BLOCK
+        cb_cols = max(win // (D * 4), self.MIN_CB_COLS)
+        n_cb = (self.n_cols + cb_cols - 1) // cb_cols
+        ldeg = deg[long_rows]
+        is_hub = ldeg >= epb * n_cb
+        hub_slots = torch.nonzero(is_hub).flatten()       # indices into long_rows
+        mid_slots = torch.nonzero(~is_hub).flatten()
+        parts_start, parts_cnt, parts_row = [], [], []
+        if hub_slots.numel():
+            hrows = long_rows[hub_slots]
+            nh = hrows.numel()
+            lo = self.rowptr[hrows].unsqueeze(1).expand(nh, n_cb + 1).clone()
+            hi = self.rowptr[hrows + 1].unsqueeze(1).expand(nh, n_cb + 1).clone()
+            target = (torch.arange(n_cb + 1, device=dev, dtype=torch.int64) * cb_cols).unsqueeze(0)
+            steps = int(ldeg.max().item()).bit_length() + 1
+            last = self.nnz - 1
+            for _ in range(steps):  # vectorised lower_bound of every block boundary in every hub row
+                mid = (lo + hi) >> 1
+                go = (self.col[mid.clamp(max=last)].to(torch.int64) < target) & (lo < hi)
+                lo = torch.where(go, mid + 1, lo)
+                hi = torch.where(go, hi, mid)
+            pos = lo  # [nh, n_cb+1]: first edge of the row with column >= b * cb_cols
+            del lo, hi, mid, go
+            cs = pos[:, :-1].t().reshape(-1)               # block-major flattening
+            cc = (pos[:, 1:] - pos[:, :-1]).t().reshape(-1)
+            cr = hub_slots.repeat(n_cb)
+            keep = cc > 0
+            parts_start.append(cs[keep]); parts_cnt.append(cc[keep]); parts_row.append(cr[keep])
+        if mid_slots.numel():
+            mrows = long_rows[mid_slots]
+            parts_start.append(self.rowptr[mrows]); parts_cnt.append(deg[mrows]); parts_row.append(mid_slots)
+        cell_start = torch.cat(parts_start)
+        cell_cnt = torch.cat(parts_cnt)
+        cell_row = torch.cat(parts_row)
+        pieces = (cell_cnt + self.seg_len - 1) // self.seg_len   # cap a segment at seg_len edges
+        seg_cell = torch.repeat_interleave(torch.arange(cell_cnt.numel(), device=dev), pieces)
+        first = torch.cumsum(pieces, 0) - pieces
+        piece_idx = torch.arange(seg_cell.numel(), device=dev) - first[seg_cell]
+        seg_start = cell_start[seg_cell] + piece_idx * self.seg_len
+        seg_end = torch.minimum(seg_start + self.seg_len, (cell_start + cell_cnt)[seg_cell])
+        seg_row = cell_row[seg_cell]
+        self.n_seg = int(seg_start.numel())
+        self.n_hub = int(hub_slots.numel())
+        if self.n_seg >= 2 ** 31:
+            raise ValueError("too many long-row segments")
+        # per row, segments in ascending edge order = fixed summation order
+        order = torch.sort(seg_row * (self.nnz + 1) + seg_start, stable=True).indices
+        counts = torch.bincount(seg_row, minlength=self.n_long)
+        segptr = torch.zeros(self.n_long + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=segptr[1:])
+        self.long_segptr = segptr.to(torch.int32)
+        self.seg_start = seg_start.contiguous()
+        self.seg_count = (seg_end - seg_start).to(torch.int32).contiguous()
+        self.row_seg = order.to(torch.int32).contiguous()
 
     def plan(self, D: int):
         """ctypes pointer to a spex_long_plan for embedding width D (NULL if no long rows)."""
@@ -123,7 +195,10 @@ class DeviceGraph:
         if self._plan_D != D:
             partial = torch.empty(self.n_seg * D, dtype=torch.float32, device=self.device)
             st = LongPlan(self.seg_len, self.n_long, self.n_seg, 0, self.long_rows.data_ptr(),
-                          self.long_segptr.data_ptr(), partial.data_ptr())
+                          self.long_segptr.data_ptr(), partial.data_ptr(),
+                          self.seg_start.data_ptr() if self.seg_start is not None else None,
+                          self.seg_count.data_ptr() if self.seg_count is not None else None,
+                          self.row_seg.data_ptr() if self.row_seg is not None else None)
             self._plan_tensors = partial
             self._plan_struct = st
             self._plan_D = D

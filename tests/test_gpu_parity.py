@@ -47,6 +47,41 @@ def test_spmm_matches_sparse_mm(cuda_device, D, seg_len):
     assert rel_err(Z, (add * 2 + ref) * 0.25) < TOL
 
 
+@pytest.mark.parametrize("seg_len", [32, 256])
+def test_spmm_column_blocked_long_rows(cuda_device, seg_len, monkeypatch):
+    """Long rows cut at column-block boundaries and launched block-major (the L2-window path used
+    on tables far larger than L2), forced here on a small graph."""
+    from spex_b200 import ops
+
+    monkeypatch.setattr(ops.DeviceGraph, "L2_WINDOW_BYTES", 16 * 1024)
+    monkeypatch.setattr(ops.DeviceGraph, "MIN_CB_COLS", 48)
+    monkeypatch.setattr(ops.DeviceGraph, "HUB_EDGES_PER_BLOCK", 10)   # hubs blocked, the rest fixed-length
+    nu, m, D = 900, 500, 64
+    u, i = random_graph(nu, m, 12000, 13, hub_items=4, hub_degree=700)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    assert g.seg_start is not None and g.n_long > 0 and g.n_seg > g.n_long and g.n_hub > 0
+    if seg_len == 32:
+        assert g.n_hub < g.n_long   # mixed plan: blocked hubs + fixed-length mid rows
+    # every edge of every long row is covered exactly once, segments never exceed seg_len
+    cnt = g.seg_count.cpu().numpy()
+    assert cnt.max() <= seg_len and cnt.min() >= 1
+    deg = (g.rowptr[1:] - g.rowptr[:-1])[g.long_rows.long()].cpu().numpy()
+    segptr = g.long_segptr.cpu().numpy()
+    per_row = np.add.reduceat(cnt[g.row_seg.cpu().numpy()], segptr[:-1])
+    assert np.array_equal(per_row, deg)
+    torch.manual_seed(0)
+    X = torch.randn(nu + 1 + m, D)
+    ref = torch.sparse.mm(A, X)
+    Y = ops.spmm(g, X.to(cuda_device))
+    assert rel_err(Y, ref) < TOL
+    assert torch.equal(Y, ops.spmm(g, X.to(cuda_device)))
+    E = X * 0.1
+    ru, ri = O.computer(E[: nu + 1], E[nu + 1:], A, 3)
+    out = ops.propagate_mean(E.to(cuda_device), g, 3)
+    assert rel_err(out, torch.cat([ru, ri])) < TOL
+
+
 @pytest.mark.parametrize("K", [0, 1, 2, 3, 4])
 def test_propagate_mean_and_determinism(cuda_device, K):
     from spex_b200 import ops
