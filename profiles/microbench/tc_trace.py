@@ -19,9 +19,9 @@ ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, 20, users, None, None)
 torch.cuda.synchronize()
 t = trace.cpu().view(64, 8).numpy()
 base = t[0, 0]
-print("tile  mma_free  mma_issued | acc_ready  drained  reduced   (cycles since tile 2000's buffer-free)")
+print("tile | MMA thread: loop_top  B_tile_ready  buffer_free  chain_issued | epilogue warp 2: acc_ready  drained   (cycles)")
 for i in range(0, 40):
     r = t[i] - base
-    print(f"{2000+i:5d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d}   chain->ready {r[2]-r[0]:5d}  ld phase {r[3]-r[2]:5d}  last reduce {r[4]-r[3]:5d}")
+    print(f"{2000+i:5d} | {r[5]:8d} {r[6]:8d} {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d}   wait_B {r[6]-r[5]:5d} wait_buf {r[0]-r[6]:5d} issue {r[1]-r[0]:4d} ->ready {r[2]-r[1]:4d} epilogue {r[3]-r[2]:5d}")
 d = t[1:40, 0] - t[0:39, 0]
 print("mean period per tile:", d.mean())

@@ -308,8 +308,8 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
                      long long* __restrict__ trace) {
   constexpr int CAP = 32 * EPL;
   // bring-up instrumentation (trace == nullptr in production): CTA 0 records clock64 stamps of
-  // tiles [kTraceT0, kTraceT0 + 64): [t][0..1] MMA thread (buffer free, chain issued),
-  // [t][2..4] epilogue warp 2 (accumulator ready, accumulator drained, tile reduced)
+  // tiles [kTraceT0, kTraceT0 + 64): MMA thread [t][5] loop top, [6] B tile landed, [0] TMEM
+  // buffer free, [1] chain issued; epilogue warp 2 [t][2] accumulator ready, [3] drained
   constexpr int kTraceT0 = 2000;
   const bool tracing = trace != nullptr && blockIdx.x == 0;
   constexpr uint32_t lbo = 128, sbo = 1024;   // layout written by spex_pack_bf16 (D = 64)
@@ -388,10 +388,12 @@ score_topk_tc_kernel(const uint8_t* __restrict__ Ub, const uint8_t* __restrict__
       for (int t = 0; t < n_item_tiles; ++t) {
         const int buf = t & 1;
         const uint32_t use = (uint32_t)(t >> 1) & 1u;
+        const bool tr = tracing && t >= kTraceT0 && t < kTraceT0 + 64;
+        if (tr) trace[(t - kTraceT0) * 8 + 5] = clock64();
         mbar_wait(&bar_full[s], ph);
+        if (tr) trace[(t - kTraceT0) * 8 + 6] = clock64();
         mbar_wait(&bar_tempty[buf], use ^ 1u);
         tc_fence_after();
-        const bool tr = tracing && t >= kTraceT0 && t < kTraceT0 + 64;
         if (tr) trace[(t - kTraceT0) * 8 + 0] = clock64();
         const uint32_t b_addr = smem_u32(sB + (size_t)s * B_BYTES);
 #pragma unroll
