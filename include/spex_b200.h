@@ -174,6 +174,16 @@ int spex_expert_gate_f32(const float* E0, const float* Eout, const float* W, int
                          int32_t D, float* out, void* stream);
 
 /*
+ * Backward of spex_expert_gate_f32 (the gate weights att_exp1/att_exp2 are trained,
+ * main_11.py:62-71): given g = dL/dout, writes dE0, dEout [n, D] and dW [2D, 2].  dW is reduced
+ * in a fixed order without atomics through `work` (fp32 [SPEX_GATE_BWD_BLOCKS * 512]).  D <= 128.
+ */
+#define SPEX_GATE_BWD_BLOCKS 1184
+int spex_expert_gate_bwd_f32(const float* E0, const float* Eout, const float* W, const float* g,
+                             int64_t n, int32_t D, float* dE0, float* dEout, float* dW, float* work,
+                             void* stream);
+
+/*
  * Full-ranking top-k, exact fp32 SIMT path:  for each of B users, the k best items of
  * <U[users[b]], I[j]>, j in [0, m_items), excluding the user's training items
  * (mask_rowptr int64 [n_mask_rows+1], mask_col int32 ascending per row: CSR of R; NULL = none).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "spex_bpr_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "spex_adam_f32": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i32, _p]),
     "spex_expert_gate_f32": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p]),
+    "spex_expert_gate_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "spex_score_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i64, _i64, _p, _p, _i32, _p, _p, _p]),
     "spex_rating_f32": (C.c_int, [_p, _p, _i32, _p, _i64, _i64, _i32, _p, _p]),
     "spex_pack_bf16": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p]),

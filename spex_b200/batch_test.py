@@ -60,7 +60,8 @@ def test(model, testRatings, testNegatives):
     if not users:
         return result
     cand = _candidate_matrix(users, testRatings, testNegatives)
-    all_users, all_items = model.computer()  # ONE propagation
+    # ONE propagation (+ gate for the multi-task model): the table forward(flag=1) scores against
+    all_users, all_items = getattr(model, "final_embeddings", model.computer)()
     if cand is not None:
         scores = ops.score_candidates(all_users, all_items, np.asarray(users, np.int64),
                                       torch.from_numpy(cand)).cpu().numpy()

@@ -296,6 +296,103 @@ expert_gate_kernel(const float* __restrict__ E0, const float* __restrict__ Eout,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// expert gating backward (autograd of model_expert_s.py:154-161; the gate weights att_exp1/2 are
+// trained in main_11.py:69).  Per row: z = [e0|e1].W, a = softmax(z), out = a0 e0 + a1 e1.
+//   da_j = <g, e_j>;  dz_j = a_j (da_j - sum_k a_k da_k)
+//   de0 = a0 g + W[0:D,:] dz;  de1 = a1 g + W[D:2D,:] dz;  dW[d, j] = sum_rows e[d] dz_j
+// dW is reduced without atomics: every warp owns a fixed strided set of rows and keeps its 16
+// partial sums in registers; the warps of a CTA are added in warp order, the CTAs in CTA order.
+constexpr int kGateBlocks = SPEX_GATE_BWD_BLOCKS;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+expert_gate_bwd_kernel(const float* __restrict__ E0, const float* __restrict__ E1,
+                       const float* __restrict__ W, const float* __restrict__ G, int64_t n, int D,
+                       float* __restrict__ dE0, float* __restrict__ dE1, float* __restrict__ work) {
+  __shared__ float sh[kWarpsPerCta][16 * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = lane * 4;
+  const bool act = d < D;
+  float2 wa[4], wb[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    wa[q] = act ? *reinterpret_cast<const float2*>(W + 2 * (d + q)) : make_float2(0.f, 0.f);
+    wb[q] = act ? *reinterpret_cast<const float2*>(W + 2 * (D + d + q)) : make_float2(0.f, 0.f);
+  }
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < n;
+       row += (int64_t)gridDim.x * kWarpsPerCta) {
+    float4 a4 = f4_zero(), b4 = f4_zero(), g4 = f4_zero();
+    if (act) {
+      a4 = *reinterpret_cast<const float4*>(E0 + row * D + d);
+      b4 = *reinterpret_cast<const float4*>(E1 + row * D + d);
+      g4 = *reinterpret_cast<const float4*>(G + row * D + d);
+    }
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float l0 = 0.f, l1 = 0.f, da0 = 0.f, da1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      l0 = fmaf(a[q], wa[q].x, l0);
+      l1 = fmaf(a[q], wa[q].y, l1);
+      l0 = fmaf(b[q], wb[q].x, l0);
+      l1 = fmaf(b[q], wb[q].y, l1);
+      da0 = fmaf(g[q], a[q], da0);
+      da1 = fmaf(g[q], b[q], da1);
+    }
+    l0 = warp_sum(l0);
+    l1 = warp_sum(l1);
+    da0 = warp_sum(da0);
+    da1 = warp_sum(da1);
+    const float mx = fmaxf(l0, l1);
+    const float x0 = expf(l0 - mx), x1 = expf(l1 - mx);
+    const float p0 = x0 / (x0 + x1), p1 = x1 / (x0 + x1);
+    const float sdot = p0 * da0 + p1 * da1;
+    const float dz0 = p0 * (da0 - sdot), dz1 = p1 * (da1 - sdot);
+    if (act) {
+      float o0[4], o1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o0[q] = p0 * g[q] + wa[q].x * dz0 + wa[q].y * dz1;
+        o1[q] = p1 * g[q] + wb[q].x * dz0 + wb[q].y * dz1;
+        acc[4 * q + 0] = fmaf(a[q], dz0, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(a[q], dz1, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(b[q], dz0, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(b[q], dz1, acc[4 * q + 3]);
+      }
+      *reinterpret_cast<float4*>(dE0 + row * D + d) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<float4*>(dE1 + row * D + d) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sh[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  // CTA partial in warp order; layout of work: [block][i = 4*q + {a.z0,a.z1,b.z0,b.z1}][lane]
+  for (int i = threadIdx.x; i < 16 * 32; i += kWarpsPerCta * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) t += sh[w][i];
+    work[(size_t)blockIdx.x * 512 + i] = t;
+  }
+}
+
+// dW[2D, 2]: sum the CTA partials in CTA order (one thread per output element)
+__global__ void __launch_bounds__(256)
+expert_gate_dw_kernel(const float* __restrict__ work, int n_blocks, int D, float* __restrict__ dW) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;   // o = 2 * row + j, row in [0, 2D)
+  if (o >= 4 * D) return;
+  const int j = o & 1, r = o >> 1;
+  const int tab = r >= D ? 1 : 0, dd = r - tab * D;
+  const int lane = dd >> 2, q = dd & 3;
+  const int i = 4 * q + 2 * tab + j;
+  float t = 0.f;
+  for (int b = 0; b < n_blocks; ++b) t += work[(size_t)b * 512 + i * 32 + lane];
+  dW[o] = t;
+}
+
 // ------------------------------------------------------------------------------------------------
 // score[u,c] = <U[users[u]], I[cand[u,c]]>: warp per (u,c)
 template <int NV>
@@ -481,5 +578,23 @@ extern "C" int spex_score_candidates_f32(const float* U, const float* I, int32_t
   else
     score_candidates_kernel<4><<<warp_grid(total), kWarpsPerCta * 32, 0, st>>>(U, I, D, users, cand, n_u, n_c, score);
   count_launch();
+  return check_last();
+}
+
+extern "C" int spex_expert_gate_bwd_f32(const float* E0, const float* Eout, const float* W,
+                                        const float* g, int64_t n, int32_t D, float* dE0,
+                                        float* dEout, float* dW, float* work, void* stream) {
+  SPEX_RETURN_IF(!E0 || !Eout || !W || !g || !dE0 || !dEout || !dW || !work || n < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 128, SPEX_E_BADDIM);
+  SPEX_RETURN_IF(!aligned16(E0) || !aligned16(Eout) || !aligned16(g) || !aligned16(dE0) ||
+                     !aligned16(dEout) || ((uintptr_t)W & 7),
+                 SPEX_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (blocks > kGateBlocks) blocks = kGateBlocks;
+  if (blocks < 1) blocks = 1;
+  expert_gate_bwd_kernel<<<(unsigned)blocks, kWarpsPerCta * 32, 0, st>>>(E0, Eout, W, g, n, D, dE0, dEout, work);
+  expert_gate_dw_kernel<<<(4 * D + 255) / 256, 256, 0, st>>>(work, (int)blocks, D, dW);
+  count_launch(2);
   return check_last();
 }

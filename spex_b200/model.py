@@ -149,21 +149,34 @@ class LightGCN(BasicModel):
     # ---- propagation ---------------------------------------------------------------------------
     def _propagate(self) -> torch.Tensor:
         """[N, D] layer-mean embeddings; rows [0, n_users] users, the rest items."""
-        if self._freeze and self._frozen_out is not None:
-            return self._frozen_out
         g = self.device_graph()
         table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
         val = valT = None
         if self.args_r.dropout and self.training:
             val, valT = self._dropout_values(g)
-        out = ops.propagate_mean(table, g, self.n_layers, val, valT)
+        return ops.propagate_mean(table, g, self.n_layers, val, valT)
+
+    def _compute_final(self) -> torch.Tensor:
+        """The [N, D] table forward() scores against (subclasses add the expert gate)."""
+        return self._propagate()
+
+    def _final(self) -> torch.Tensor:
+        if self._freeze and self._frozen_out is not None:
+            return self._frozen_out
+        out = self._compute_final()
         if self._freeze:
             self._frozen_out = out.detach()
         return out
 
     def computer(self):
         """propagate methods for lightGCN: returns (users [n_users+1, D], items [m_items, D])."""
-        out = self._propagate()
+        out = self._final() if type(self)._compute_final is LightGCN._compute_final else self._propagate()
+        return out[: self.n_user_rows], out[self.n_user_rows:]
+
+    def final_embeddings(self):
+        """(users, items) of the table forward() scores against: computer() for this model, the
+        expert-gated tables for the multi-task model.  The hoisted Test() ranks with these."""
+        out = self._final()
         return out[: self.n_user_rows], out[self.n_user_rows:]
 
     @contextlib.contextmanager
@@ -182,7 +195,7 @@ class LightGCN(BasicModel):
     def forward(self, users, items, labels, flag=0):
         if flag not in (0, 1):
             raise UnboundLocalError("loss")  # the reference falls through to `return loss` unbound
-        out = self._propagate()
+        out = self._final()
         if flag == 1:
             return ops.gather_dot(out, self.n_user_rows, users, items)
         return ops.bce_loss(out, self.n_user_rows, users, items, labels)
@@ -191,7 +204,7 @@ class LightGCN(BasicModel):
     def bpr_loss(self, users, pos, neg):
         """(loss, reg_loss): mean softplus(<u,n> - <u,p>) and 0.5*(|u0|^2+|p0|^2+|n0|^2)/B with
         u,p,n from computer() and u0,p0,n0 the raw embedding rows."""
-        out = self._propagate()
+        out = self._final()
         table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
         return ops.bpr_loss(out, table, self.n_user_rows, users, pos, neg)
 

@@ -489,14 +489,37 @@ def score_topk_bf16(Ub, B, B_pad, Ib, m_items, m_pad, k, user_ids=None, mask_row
     return out_idx, out_val
 
 
+GATE_BWD_BLOCKS = 1184  # SPEX_GATE_BWD_BLOCKS in include/spex_b200.h
+
+
+class _ExpertGate(torch.autograd.Function):
+    """out = a0*E0 + a1*Eout, a = softmax([E0|Eout].W) per row (model_expert_s.py:154-161)."""
+
+    @staticmethod
+    def forward(ctx, E0, Eout, W):
+        _need_cuda(E0, Eout, W)
+        E0, Eout, W = _f32c(E0), _f32c(Eout), _f32c(W)
+        out = torch.empty_like(E0)
+        call("spex_expert_gate_f32", ptr(E0), ptr(Eout), ptr(W), E0.shape[0], E0.shape[1], ptr(out),
+             stream_ptr())
+        ctx.save_for_backward(E0, Eout, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        E0, Eout, W = ctx.saved_tensors
+        g = _f32c(g)
+        dE0, dE1 = torch.empty_like(E0), torch.empty_like(Eout)
+        dW = torch.empty_like(W)
+        work = torch.empty(GATE_BWD_BLOCKS * 512, dtype=torch.float32, device=E0.device)
+        call("spex_expert_gate_bwd_f32", ptr(E0), ptr(Eout), ptr(W), ptr(g), E0.shape[0], E0.shape[1],
+             ptr(dE0), ptr(dE1), ptr(dW), ptr(work), stream_ptr())
+        return dE0, dE1, dW
+
+
 def expert_gate(E0, Eout, W):
-    """softmax([E0|Eout].W) convex mix per row (model_expert_s.py:154-161), forward only."""
-    _need_cuda(E0, Eout, W)
-    E0, Eout, W = _f32c(E0), _f32c(Eout), _f32c(W)
-    out = torch.empty_like(E0)
-    call("spex_expert_gate_f32", ptr(E0), ptr(Eout), ptr(W), E0.shape[0], E0.shape[1], ptr(out),
-         stream_ptr())
-    return out
+    """softmax([E0|Eout].W) convex mix per row (model_expert_s.py:154-161), differentiable."""
+    return _ExpertGate.apply(E0, Eout, W)
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step):

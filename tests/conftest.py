@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# golden data (tiny/trust/test2.txt is a pickle in the reference's file naming) is not test code
+collect_ignore_glob = ["golden/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 

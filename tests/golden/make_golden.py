@@ -63,11 +63,88 @@ def write_dataset(root):
             f.write(" ".join([str(u)] + [str(int(x)) for x in negs]) + "\n")
 
 
+def write_trust(root, n_users):
+    """Synthetic trust paths in the pickle layout main_11.py:31-32 reads:
+    train.txt = (paths, targets); test2.txt = (paths, targets, candidates with the positive LAST)."""
+    import pickle
+
+    rng = np.random.default_rng(99)
+    tdir = os.path.join(root, "trust")
+    os.makedirs(tdir, exist_ok=True)
+
+    def paths(n_per_user):
+        P, T = [], []
+        for u in range(n_users):
+            for _ in range(n_per_user):
+                L = int(rng.integers(1, 6))
+                p = [u] + [int(x) for x in rng.integers(0, n_users, L - 1)]
+                P.append(p)
+                T.append(int(rng.integers(0, n_users)))
+        return P, T
+
+    P, T = paths(3)
+    pickle.dump((P, T), open(os.path.join(tdir, "train.txt"), "wb"))
+    P2, T2 = paths(1)
+    negs = []
+    for t in T2:
+        cand = [x for x in range(n_users) if x != t]
+        negs.append([int(x) for x in rng.choice(cand, size=49, replace=False)] + [t])
+    pickle.dump((P2, T2, negs), open(os.path.join(tdir, "test2.txt"), "wb"))
+
+
+def make_expert_golden(args, dataset, work):
+    """Multi-task model (utility1/model_expert_s.py) on the tiny dataset + synthetic trust paths."""
+    import pickle
+    import utility1.model_expert_s as ref_me
+    import utility1.batch_test as ref_bt
+    import utility1.utils as ref_utils
+    from utility2.utils import Data
+    from utility2.batch_test_gnn import trust_test5
+
+    tdir = os.path.join(HERE, DS, "trust")
+    train_raw = pickle.load(open(os.path.join(tdir, "train.txt"), "rb"))
+    test_raw = pickle.load(open(os.path.join(tdir, "test2.txt"), "rb"))
+    train_paths = Data(train_raw, dataset.n_users, shuffle=False)
+    test_paths = Data(test_raw, dataset.n_users, shuffle=False, test=True)
+    args.batchSize = 32
+    ref_utils.set_seed(2020)
+    model = ref_me.LightGCN(args, dataset)
+    E = {}
+    for k, v in model.state_dict().items():
+        E["sd." + k] = v.detach().numpy().copy()
+    rng = np.random.default_rng(11)
+    B = 64
+    users = rng.integers(0, dataset.n_users, B)
+    items = rng.integers(0, dataset.m_items, B)
+    labels = rng.integers(0, 2, B)
+    sl = rng.choice(len(train_raw[0]), size=40, replace=False)
+    E["users"], E["items"], E["labels"], E["slice"] = users, items, labels, sl
+    model.train()
+    model.zero_grad()
+    l1, l2 = model(torch.from_numpy(users), torch.from_numpy(items), torch.from_numpy(labels), sl, train_paths, flag=0)
+    (l1 + l2).backward()
+    E["loss1"], E["loss2"] = np.float32(l1.item()), np.float32(l2.item())
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            E["grad." + name] = p.grad.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        E["gamma"] = model(torch.from_numpy(users), torch.from_numpy(items), None, None, None, flag=1).numpy().copy()
+        sc, negs = model(None, None, None, np.arange(10), test_paths, 2)
+        E["trust_scores"] = sc.numpy().copy()
+        ret = ref_bt.rec_test(model, dataset.testRatings, dataset.testNegatives)
+        E["rec_recall"], E["rec_ndcg"] = ret["recall"], ret["ndcg"]
+        E["trust_metrics"] = np.array(trust_test5(model, test_paths))
+    np.savez_compressed(os.path.join(HERE, "expert_tiny.npz"), **E)
+    print("wrote expert_tiny.npz: loss1 %.6f loss2 %.6f trust %s" % (E["loss1"], E["loss2"], E["trust_metrics"]))
+
+
 def main():
     out_ds = os.path.join(HERE, DS)
     if os.path.exists(out_ds):
         shutil.rmtree(out_ds)
     write_dataset(out_ds)
+    write_trust(out_ds, 60)
 
     work = tempfile.mkdtemp(prefix="spex_golden_")
     os.makedirs(os.path.join(work, "code"))
@@ -189,6 +266,7 @@ def main():
     G["gate_out"] = (torch.mul(e0, att[:, 0].unsqueeze(1)) + torch.mul(ex, att[:, 1].unsqueeze(1))).numpy()
 
     np.savez_compressed(os.path.join(HERE, "lightgcn_tiny.npz"), **G)
+    make_expert_golden(args, dataset, work)
     shutil.rmtree(work)
     print("wrote", os.path.join(HERE, "lightgcn_tiny.npz"), "keys:", len(G))
     print("test_recall", G["test_recall"], "bce_loss", G["bce_loss"], "nnz", A._nnz())
