@@ -309,10 +309,16 @@ def run_ours(args):
     alg_bytes = (local_nnz + local_rows) * (8 + 4 * D)
     t_launch = ms_step * 1e-3 / K_LAYERS
     achieved = alg_bytes / t_launch / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8> (+long-row passes)", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_kind": peak_kind,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "per-launch time = step time / K (exchange included at N>1)"}
+    # DRAM traffic per layer from the round's `ncu --set full` capture of this exact workload
+    # (profiles/r01_ncu_spmm_final.json: rows 244.92+7.57, segments 126.53+0.52, fix 0.60+0.02 GB):
+    # 380.2 GB, i.e. 0.72 of the algorithmic bytes - L2 re-use of popular item rows, no re-reads.
+    traffic = 380.16e9 if (world == 1 and args.scale == 1.0) else None
+    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8> + spmm_seg_list_kernel<64,8> + "
+                                          "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "per-launch time = step time / K (exchange included at N>1); traffic from ncu, "
+                        "per layer"}
 
     # ---- e2e: host tables in, host tables out, through the public operator ----
     e2e = None
@@ -387,7 +393,9 @@ def run_ours(args):
                  "unit": "users/s", "users_per_step_per_gpu": n_eval, "m_items": m, "ms_per_step": ms_ev,
                  "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": tf,
                               "peak": tc_burst, "unit": "TFLOP/s", "frac": tf / tc_burst,
-                              "peak_kind": peak_kind, "traffic": None}}
+                              "peak_kind": peak_kind,
+                              "traffic": 761.8e6 if (world == 1 and args.scale == 1.0 and
+                                                     n_eval == 148 * 2 * 128) else None}}
 
     launches_total = _capi.launch_count() - launches0
     ck = clocks.stop() if clocks else None
