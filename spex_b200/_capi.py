@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspex_b200.so")
+LIB_PATH = os.environ.get("SPEX_B200_LIB") or os.path.join(_HERE, "libspex_b200.so")  # env: tuning builds
 
 _p = C.c_void_p
 _i32 = C.c_int32

@@ -127,7 +127,17 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
   }
 }
 
-constexpr int kRowsPerCta = 8;  // 8 warps = 256 threads
+#ifndef SPEX_ROWS_PER_CTA
+#define SPEX_ROWS_PER_CTA 1
+#endif
+#ifndef SPEX_U64
+#define SPEX_U64 8
+#endif
+// One warp per CTA: measured on the 1B-interaction graph (K=3 step, ms): 8 warps/CTA 230.5, 4: 224.7,
+// 2: 221.6, 1: 186.9 (U=8).  A CTA retires only when its slowest row is done, so with degrees from 1
+// to 1024 multi-warp CTAs strand resident-warp slots; single-warp CTAs let the block scheduler
+// backfill every slot (32 CTAs = 32 warps per SM at 63 registers).
+constexpr int kRowsPerCta = SPEX_ROWS_PER_CTA;  // warps (= rows) per CTA
 
 template <int D, int U>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
@@ -320,7 +330,7 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
   if (n_rows == 0) return 0;
   switch (D) {
     case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st);
-    case 64: return launch_vec<64, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
+    case 64: return launch_vec<64, SPEX_U64>(rowptr, col, val, X, n_rows, ep, plan, st);
     case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
     default: break;
   }
