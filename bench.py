@@ -215,6 +215,8 @@ def run_ours(args):
     keys = synthetic.generate_interactions(nu, m, ni, seed=2020, device=dev)
     g, mask_rp, mask_col = synthetic.build_norm_adj_device(keys, nu, m)
     del keys
+    n_hot = 0 if os.environ.get("SPEX_NO_HOT") else g.mark_hot_columns(
+        D, budget_bytes=(int(os.environ["SPEX_HOT_MB"]) << 20) if os.environ.get("SPEX_HOT_MB") else None)
     nnz = g.nnz
     table = synthetic.xavier_table(nur, m, D, 2020, dev)
     torch.cuda.synchronize()
@@ -253,7 +255,7 @@ def run_ours(args):
             r0, r1 = bounds[rank], bounds[rank + 1]
             lo, hi = int(rp_host[r0]), int(rp_host[r1])
             lg = ops.DeviceGraph((g.rowptr[r0: r1 + 1] - lo).contiguous(), g.col[lo:hi], g.val[lo:hi], N,
-                                 None, g.seg_len, row_offset=r0)
+                                 None, g.seg_len, row_offset=r0, col_hot=g.col_hot)
             if it == 2:
                 break
             y = torch.empty(r1 - r0, D, dtype=torch.float32, device=dev)
@@ -273,7 +275,8 @@ def run_ours(args):
             balance_log.append([round(x, 3) for x in times])
             bounds = rebalance_bounds(rp_host, bounds, times)
             del y, lg
-        lg = ops.DeviceGraph(lg.rowptr, lg.col.clone(), lg.val.clone(), N, None, g.seg_len, row_offset=r0)
+        lg = ops.DeviceGraph(lg.rowptr, lg.col.clone(), lg.val.clone(), N, None, g.seg_len, row_offset=r0,
+                             col_hot=g.col_hot)
         E0_local = table[r0:r1].clone()
         del g, table
         torch.cuda.empty_cache()
@@ -458,7 +461,7 @@ def run_ours(args):
                        "edges_definition": "nnz(A) = 2*|R| per layer", "l2": "inputs larger than L2 (no flush needed)"
                        if nnz * 8 > 200e6 else "inputs smaller than L2: timing is L2-warm",
                        "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" if world > 1 else ""),
-                       "graph_build_s": round(t_gen, 2),
+                       "graph_build_s": round(t_gen, 2), "hot_rows_kept_in_l2": n_hot,
                        "balance_ms_per_rank": balance_log if world > 1 else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,

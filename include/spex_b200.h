@@ -54,11 +54,16 @@ int64_t spex_launch_count(void);
  * The plan is built once per graph by the host (spex_b200/ops.py: DeviceGraph) and passed to every
  * SpMM as a HOST struct holding device pointers; NULL (or n_long == 0) means "no long rows".
  * ------------------------------------------------------------------------------------------ */
+/* flags: bit 31 of every col[] entry marks a HOT table row (one that is gathered so often that it
+ * should stay in L2): the kernels strip the bit and gather hot rows with the L2 evict_last policy,
+ * all others with evict_first.  A plan with n_long == 0 may still carry this flag. */
+#define SPEX_PLAN_COL_HOTBIT 1
+
 typedef struct spex_long_plan {
   int32_t seg_len;            /* rows with degree > seg_len take the long-row path (>= 32)    */
   int32_t n_long;             /* number of such rows                                          */
   int32_t n_seg;              /* total number of segments                                     */
-  int32_t reserved;
+  int32_t flags;              /* SPEX_PLAN_* bits                                             */
   const int32_t* long_rows;   /* int32 [n_long]    row ids, ascending                         */
   const int32_t* long_segptr; /* int32 [n_long+1]  exclusive scan of segments per long row    */
   float* partial;             /* fp32  [n_seg, D]  workspace                                  */

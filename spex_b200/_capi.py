@@ -25,7 +25,7 @@ class LongPlan(C.Structure):
         ("seg_len", _i32),
         ("n_long", _i32),
         ("n_seg", _i32),
-        ("reserved", _i32),
+        ("flags", _i32),
         ("long_rows", _p),
         ("long_segptr", _p),
         ("partial", _p),

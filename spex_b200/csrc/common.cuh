@@ -46,6 +46,26 @@ __device__ __forceinline__ float4 ld_gather_f4(const float* p) {
                : "l"(p));
   return v;
 }
+// Software-managed L2 residency: hot embedding rows (columns flagged by the graph plan) are loaded
+// with an evict_last policy, everything else with evict_first, so the 126 MB L2 keeps the rows that
+// are gathered thousands of times instead of whatever was touched most recently.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_gather_f4_hint(const float* p, uint64_t policy) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "l"(policy));
+  return v;
+}
 // plain (coherent) 128-bit load: for buffers that the same kernel also writes (in-place Z).
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   return *reinterpret_cast<const float4*>(p);

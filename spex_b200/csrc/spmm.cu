@@ -35,7 +35,9 @@ struct RowShape {
 // partial rows); 2: col[e] from the list, val[e] = 1 (sum of listed partial rows).
 // kFirst: the first 32 edges' (col, val) were loaded by the caller (c0, v0) while the previous row
 // was being reduced (software prefetch in the persistent kernels).
-template <int D, int U, int kMode, bool kFirst = false>
+// kHot: bit 31 of a column index flags a hot table row (spex_long_plan.flags & SPEX_PLAN_COL_HOTBIT):
+// hot rows are gathered with the L2 evict_last policy, the rest with evict_first.
+template <int D, int U, int kMode, bool kFirst = false, bool kHot = false>
 __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict__ col,
                                                       const float* __restrict__ val,
                                                       const float* __restrict__ X, int64_t start,
@@ -45,6 +47,11 @@ __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict_
   const int grp = lane / LPR, sub = lane % LPR;
   const float* Xs = X + sub * 4;
   float4 acc = f4_zero();
+  uint64_t pol_last = 0, pol_first = 0;
+  if (kHot) {
+    pol_last = l2_policy_evict_last();
+    pol_first = l2_policy_evict_first();
+  }
   for (int64_t base = start; base < end; base += 32) {
     const int64_t e = base + lane;
     int c = 0;
@@ -75,7 +82,10 @@ __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict_
         const int cc = __shfl_sync(kFull, c, idx & 31);
         vv[u] = __shfl_sync(kFull, v, idx & 31);
         if (idx < n) {
-          x[u] = ld_gather_f4(Xs + (int64_t)cc * D);
+          if (kHot)
+            x[u] = ld_gather_f4_hint(Xs + (int64_t)(cc & 0x7fffffff) * D, cc < 0 ? pol_last : pol_first);
+          else
+            x[u] = ld_gather_f4(Xs + (int64_t)cc * D);
         } else {
           x[u] = f4_zero();
           vv[u] = 0.f;
@@ -139,7 +149,7 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
 // backfill every slot (32 CTAs = 32 warps per SM at 63 registers).
 constexpr int kRowsPerCta = SPEX_ROWS_PER_CTA;  // warps (= rows) per CTA
 
-template <int D, int U>
+template <int D, int U, bool kHot>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
@@ -149,12 +159,12 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
   if (row >= n_rows) return;
   const int64_t start = rowptr[row], end = rowptr[row + 1];
   if (skip_longer_than > 0 && end - start > skip_longer_than) return;  // long-row path
-  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, end, lane);
+  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
   row_epilogue<D>(ep, acc, row, lane);
 }
 
 // warp per segment of a long row -> partial[seg, :]
-template <int D, int U>
+template <int D, int U, bool kHot>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ X,
@@ -176,7 +186,7 @@ spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restri
   const int64_t rs = rowptr[row], re = rowptr[row + 1];
   const int64_t start = rs + (int64_t)k * seg_len;
   const int64_t end = (start + seg_len < re) ? start + seg_len : re;
-  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, end, lane);
+  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -200,7 +210,7 @@ spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
 // block-major order: at any moment the resident warps gather from one ~32 MB window of the
 // table, which the 126 MB L2 keeps resident, so each table row of the window comes from HBM once
 // instead of once per edge.  warp per (row, column block) segment -> partial[seg, :]
-template <int D, int U>
+template <int D, int U, bool kHot>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
                      const float* __restrict__ X, const int64_t* __restrict__ seg_start,
@@ -210,7 +220,7 @@ spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ 
   const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   const int64_t start = seg_start[seg];
-  const float4 acc = warp_row_accumulate<D, U, 0>(col, val, X, start, start + seg_count[seg], lane);
+  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, start + seg_count[seg], lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -282,26 +292,26 @@ spmm_rows_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
   }
 }
 
-template <int D, int U>
-static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
-                      int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
-                      cudaStream_t st) {
+template <int D, int U, bool kHot>
+static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                        int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
+                        cudaStream_t st) {
   const bool has_long = plan && plan->n_long > 0;
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
-  spmm_rows_kernel<D, U><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+  spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
       rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep);
   count_launch();
   if (has_long) {
     const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
     const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;
-    if (plan->seg_start) {   // column-blocked segmentation (block-major launch order)
-      spmm_seg_list_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
+    if (plan->seg_start) {   // explicit segment list (column-blocked hubs + fixed-length rest)
+      spmm_seg_list_kernel<D, U, kHot><<<gs, kRowsPerCta * 32, 0, st>>>(
           col, val, X, plan->seg_start, plan->seg_count, plan->n_seg, plan->partial);
       spmm_long_fix_list_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
           plan->long_rows, plan->long_segptr, plan->row_seg, plan->n_long, plan->partial, ep);
     } else {                 // fixed-length segmentation
-      spmm_long_seg_kernel<D, U><<<gs, kRowsPerCta * 32, 0, st>>>(
+      spmm_long_seg_kernel<D, U, kHot><<<gs, kRowsPerCta * 32, 0, st>>>(
           rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
           plan->seg_len, plan->partial);
       spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
@@ -310,6 +320,15 @@ static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* va
     count_launch(2);
   }
   return check_last();
+}
+
+template <int D, int U>
+static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                      int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
+                      cudaStream_t st) {
+  if (plan && (plan->flags & SPEX_PLAN_COL_HOTBIT))
+    return launch_vec_h<D, U, true>(rowptr, col, val, X, n_rows, ep, plan, st);
+  return launch_vec_h<D, U, false>(rowptr, col, val, X, n_rows, ep, plan, st);
 }
 
 int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
@@ -334,6 +353,7 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
     case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
     default: break;
   }
+  SPEX_RETURN_IF(plan && (plan->flags & SPEX_PLAN_COL_HOTBIT), SPEX_E_BADDIM);  // D in {32,64,128} only
   // generic path handles long rows serially (no plan needed; still deterministic)
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;

@@ -133,6 +133,8 @@ class LightGCN(BasicModel):
                 if isinstance(A, (list, tuple)):  # A_split row folds (dataloader.py:167-177)
                     A = _stack_row_folds(A)
                 self._dev_graph = ops.DeviceGraph.from_sparse_coo(A, dev)
+            if self._dev_graph.n_rows == self._dev_graph.n_cols:
+                self._dev_graph.mark_hot_columns(self.latent_dim)  # no-op unless the table dwarfs L2
         return self._dev_graph
 
     def _dropout_values(self, g: ops.DeviceGraph):

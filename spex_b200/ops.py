@@ -55,7 +55,7 @@ class DeviceGraph:
     """
 
     def __init__(self, rowptr, col, val, n_cols: int, tpos=None, seg_len: int = DEFAULT_SEG_LEN,
-                 row_offset: int = 0, symmetric: bool = True, D_hint: int = 64):
+                 row_offset: int = 0, symmetric: bool = True, D_hint: int = 64, col_hot: bool = False):
         _need_cuda(rowptr, col, val)
         assert rowptr.dtype == torch.int64 and col.dtype == torch.int32 and val.dtype == torch.float32
         self.rowptr, self.col, self.val = rowptr, col, val
@@ -70,6 +70,9 @@ class DeviceGraph:
         self._plan_struct = None
         self._plan_D = 0
         self._plan_tensors = None
+        self.col_hot = False          # bit 31 of col flags hot table rows (SPEX_PLAN_COL_HOTBIT)
+        if col_hot:                   # a row block cut from an already marked graph
+            self.col_hot = True
         self._build_plan(D_hint)
 
     # -- construction ---------------------------------------------------------------------------
@@ -151,7 +154,7 @@ class DeviceGraph:
             last = self.nnz - 1
             for _ in range(steps):  # vectorised lower_bound of every block boundary in every hub row
                 mid = (lo + hi) >> 1
-                go = (self.col[mid.clamp(max=last)].to(torch.int64) < target) & (lo < hi)
+                go = ((self.col[mid.clamp(max=last)] & 0x7FFFFFFF).to(torch.int64) < target) & (lo < hi)
                 lo = torch.where(go, mid + 1, lo)
                 hi = torch.where(go, hi, mid)
             pos = lo  # [nh, n_cb+1]: first edge of the row with column >= b * cb_cols
@@ -188,13 +191,57 @@ class DeviceGraph:
         self.seg_count = (seg_end - seg_start).to(torch.int32).contiguous()
         self.row_seg = order.to(torch.int32).contiguous()
 
+    HOT_L2_BYTES = 48 << 20   # table bytes flagged hot (kept in L2 by the evict_last policy)
+
+    def mark_hot_columns(self, D: int, col_degree: Optional[torch.Tensor] = None,
+                         budget_bytes: Optional[int] = None) -> int:
+        """Flag the most frequently gathered table rows in bit 31 of `col` (in place).
+
+        The kernels gather flagged rows with the L2 evict_last policy and everything else with
+        evict_first, so the hottest HOT_L2_BYTES of the table stay L2-resident.  `col_degree[c]` =
+        how many edges gather column c; for the symmetric normalised adjacency that is the row
+        degree, which is the default.  Returns the number of hot rows (0: nothing marked).
+        """
+        if self.col_hot:
+            return -1
+        budget = self.HOT_L2_BYTES if budget_bytes is None else budget_bytes
+        n_hot = min(budget // (D * 4), self.n_cols)
+        if self.n_cols * D * 4 <= 2 * budget or n_hot <= 0 or D not in (32, 64, 128):
+            return 0  # the table fits in L2 anyway / generic-D path has no hint variant
+        if col_degree is None:
+            if self.n_rows != self.n_cols:
+                raise ValueError("column degrees are needed for a non-square graph")
+            col_degree = self.rowptr[1:] - self.rowptr[:-1]
+        thr = torch.topk(col_degree, n_hot).values[-1]
+        hot = col_degree >= torch.clamp(thr, min=2)     # never flag rows that are gathered once
+        if int(hot.sum()) > 2 * n_hot:                  # a flat degree distribution: no hot set
+            return 0
+        chunk = 1 << 28
+        int_min = -(2 ** 31)
+        for s0 in range(0, self.nnz, chunk):
+            c = self.col[s0: s0 + chunk]
+            c.bitwise_or_(hot[c.long()].to(torch.int32) * int_min)
+        self.col_hot = True
+        self._plan_D = 0
+        return int(hot.sum())
+
+    def clean_col(self) -> torch.Tensor:
+        """Column indices without the hot flag."""
+        return (self.col & 0x7FFFFFFF) if self.col_hot else self.col
+
     def plan(self, D: int):
-        """ctypes pointer to a spex_long_plan for embedding width D (NULL if no long rows)."""
-        if self.n_long == 0:
+        """ctypes pointer to a spex_long_plan for embedding width D (NULL if nothing to say)."""
+        if self.n_long == 0 and not self.col_hot:
             return None
+        flags = 1 if self.col_hot else 0
+        if self.n_long == 0:
+            if self._plan_D != D:
+                self._plan_struct = LongPlan(self.seg_len, 0, 0, flags, None, None, None, None, None, None)
+                self._plan_D = D
+            return C.byref(self._plan_struct)
         if self._plan_D != D:
             partial = torch.empty(self.n_seg * D, dtype=torch.float32, device=self.device)
-            st = LongPlan(self.seg_len, self.n_long, self.n_seg, 0, self.long_rows.data_ptr(),
+            st = LongPlan(self.seg_len, self.n_long, self.n_seg, flags, self.long_rows.data_ptr(),
                           self.long_segptr.data_ptr(), partial.data_ptr(),
                           self.seg_start.data_ptr() if self.seg_start is not None else None,
                           self.seg_count.data_ptr() if self.seg_count is not None else None,
@@ -231,7 +278,7 @@ class DeviceGraph:
     def to_sparse_coo(self) -> torch.Tensor:
         deg = self.rowptr[1:] - self.rowptr[:-1]
         rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), deg)
-        idx = torch.stack([rows + self.row_offset, self.col.to(torch.int64)])
+        idx = torch.stack([rows + self.row_offset, self.clean_col().to(torch.int64)])
         return torch.sparse_coo_tensor(idx, self.val, (self.n_rows, self.n_cols), is_coalesced=True)
 
 

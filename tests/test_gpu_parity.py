@@ -82,6 +82,28 @@ def test_spmm_column_blocked_long_rows(cuda_device, seg_len, monkeypatch):
     assert rel_err(out, torch.cat([ru, ri])) < TOL
 
 
+@pytest.mark.parametrize("seg_len", [32, 1024])
+def test_hot_column_hints_do_not_change_results(cuda_device, seg_len):
+    """Bit 31 of col flags hot table rows (L2 evict_last gathers): a cache hint only, so results
+    are bit-identical to the unflagged graph."""
+    from spex_b200 import ops
+
+    nu, m, D = 900, 500, 64
+    u, i = random_graph(nu, m, 12000, 17, hub_items=4, hub_degree=700)
+    g0 = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    g1 = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    n_hot = g1.mark_hot_columns(D, budget_bytes=16 * 1024)
+    assert 0 < n_hot <= 2 * (16 * 1024 // 256) and g1.col_hot
+    assert (g1.col < 0).any() and torch.equal(g1.clean_col(), g0.col)
+    torch.manual_seed(0)
+    X = torch.randn(nu + 1 + m, D, device=cuda_device)
+    assert torch.equal(ops.spmm(g1, X), ops.spmm(g0, X))
+    E = X * 0.1
+    assert torch.equal(ops.propagate_mean(E, g1, 3), ops.propagate_mean(E, g0, 3))
+    A = g1.to_sparse_coo()
+    assert int(A.indices()[1].max()) < nu + 1 + m
+
+
 @pytest.mark.parametrize("K", [0, 1, 2, 3, 4])
 def test_propagate_mean_and_determinism(cuda_device, K):
     from spex_b200 import ops
