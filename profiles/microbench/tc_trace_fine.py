@@ -1,4 +1,5 @@
-"""Bring-up: per-tile timeline of the tcgen05 scorer (CTA 0, tiles 2000..2063), clock64 cycles."""
+"""Bring-up (library built with EXTRA=-DSPEX_TC_TRACE=2): cost of each synchronisation step of
+epilogue warp 2, tiles 2000.., in cycles."""
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
@@ -18,10 +19,8 @@ _capi.lib.spex_debug_tc_trace(ctypes.c_void_p(trace.data_ptr()))
 ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, 20, users, None, None)
 torch.cuda.synchronize()
 t = trace.cpu().view(64, 8).numpy()
-base = t[0, 0]
-print("tile | MMA thread: loop_top  B_tile_ready  buffer_free  chain_issued | epilogue warp 2: acc_ready  drained   (cycles)")
-for i in range(0, 40):
+base = t[0, 7]
+print("tile | acquire: start  poll  syncwarp  fence_after | release: start fence_before syncwarp arrive")
+for i in range(0, 24):
     r = t[i] - base
-    print(f"{2000+i:5d} | {r[5]:8d} {r[6]:8d} {r[0]:8d} {r[1]:8d} | {r[2]:8d} {r[3]:8d}   wait_B {r[6]-r[5]:5d} wait_buf {r[0]-r[6]:5d} issue {r[1]-r[0]:4d} ->ready {r[2]-r[1]:4d} epilogue {r[3]-r[2]:5d}")
-d = t[1:40, 0] - t[0:39, 0]
-print("mean period per tile:", d.mean())
+    print(f"{2000+i:5d} | {r[7]:7d} +{r[0]-r[7]:4d} +{r[1]-r[0]:4d} +{r[2]-r[1]:4d} | {r[3]:7d} +{r[4]-r[3]:4d} +{r[5]-r[4]:4d} +{r[6]-r[5]:4d}")

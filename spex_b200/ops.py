@@ -501,6 +501,7 @@ def rating_dense(U, I, users, apply_sigmoid: bool = True):
 
 
 TC_USER_MULTIPLE = 128   # users per CTA of the tcgen05 scorer (UMMA M)
+TC_MAX_K = 64            # larger k: score_topk_f32
 TC_ITEM_MULTIPLE = 128   # items per tile (UMMA N)
 
 
@@ -525,6 +526,8 @@ def score_topk_bf16(Ub, B, B_pad, Ib, m_items, m_pad, k, user_ids=None, mask_row
                     mask_col=None, out_idx=None, out_val=None):
     """tcgen05 bf16 scoring GEMM fused with train-item masking and per-row top-k (D = 64)."""
     _need_cuda(Ub, Ib)
+    if not 1 <= k <= TC_MAX_K:
+        raise ValueError(f"score_topk_bf16: k must be in [1, {TC_MAX_K}] (use score_topk_f32 beyond)")
     dev = Ub.device
     if out_idx is None:
         out_idx = torch.empty(B, k, dtype=torch.int32, device=dev)

@@ -308,7 +308,7 @@ def test_topk_bf16_tensor_core(cuda_device):
     Ub, b_pad = ops.pack_bf16(Ud, users.to(cuda_device), ops.TC_USER_MULTIPLE)
     rpd = torch.from_numpy(rp).to(cuda_device)
     cold = torch.from_numpy(col).to(cuda_device)
-    for k in (1, 20, 64):
+    for k in (1, 20, 50, ops.TC_MAX_K):
         idx, val = ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, k, users.to(cuda_device), rpd, cold)
         torch.cuda.synchronize()
         # inputs are exactly representable in bf16, so only the accumulation order differs
@@ -318,6 +318,42 @@ def test_topk_bf16_tensor_core(cuda_device):
     i16, v16 = ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, 20, users.to(cuda_device), rpd, cold)
     assert float((v32 - v16).abs().max()) < 1e-4
     assert float((i32 == i16).float().mean()) > 0.99
+
+
+def test_topk_bf16_ties_and_duplicates(cuda_device):
+    """Exact score ties (duplicated and all-zero item rows, spread over both column halves of the
+    256-item stages) are broken by ascending item id, exactly like the fp32 scorer."""
+    from spex_b200 import ops
+
+    torch.manual_seed(11)
+    n_u, m, D = 130, 3000, 64
+    U = (torch.randn(n_u, D) * 0.3).bfloat16().float()
+    base = (torch.randn(40, D) * 0.3).bfloat16().float()
+    I = base[torch.randint(0, 40, (m,))].clone()      # every item row is one of 40 vectors
+    I[::7] = 0.0                                       # and every 7th is all-zero (score 0)
+    Ud, Id = U.to(cuda_device), I.to(cuda_device)
+    users = torch.arange(n_u, device=cuda_device)
+    Ib, m_pad = ops.pack_bf16(Id, None, ops.TC_ITEM_MULTIPLE)
+    Ub, b_pad = ops.pack_bf16(Ud, users, ops.TC_USER_MULTIPLE)
+    scores = torch.matmul(U.double(), I.double().t())
+    for k in (5, 20, 50):
+        i16, v16 = ops.score_topk_bf16(Ub, n_u, b_pad, Ib, m, m_pad, k, users, None, None)
+        # reference order: score descending, then item id ascending (stable sort on -score)
+        order = torch.sort(-scores, dim=1, stable=True).indices[:, :k]
+        ref_v = torch.gather(scores, 1, order)
+        got_v = torch.gather(scores, 1, i16.cpu().long())
+        assert torch.allclose(got_v, ref_v, atol=1e-5), k            # same score multiset per rank
+        tie_free = (ref_v[:, :-1] - ref_v[:, 1:]).abs() > 1e-4
+        # within a run of equal scores the ids must ascend
+        ids = i16.cpu().long()
+        assert bool(((ids[:, 1:] > ids[:, :-1]) | tie_free).all()), k
+        # the lowest ids of a tied group win: identical to the stable order on every row whose
+        # top-(k+1) scores are either exactly tied (identical item rows) or clearly apart
+        top = -torch.sort(-scores, dim=1, stable=True).values[:, : k + 1]
+        gap = top[:, :-1] - top[:, 1:]
+        clean = ~((gap > 1e-9) & (gap < 1e-4)).any(dim=1)
+        assert int(clean.sum()) > n_u // 2
+        assert torch.equal(ids[clean], order[clean]), k
 
 
 def test_model_rank_topk_bf16_vs_fp32(cuda_device):
