@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10M x 5M x 1B workload")
     ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "push"), choices=["nccl", "push"])
+    ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE", "push"), choices=["nccl", "push"],
+                    help="how E^(0) is all-gathered in push mode")
     ap.add_argument("--eval-users", type=int, default=148 * 2 * 128)
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,6 +283,8 @@ def run_ours(args):
         del g, table
         torch.cuda.empty_cache()
         prop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
+        if args.exchange == "push":
+            prop.e0_exchange = args.e0_exchange
         local_nnz, local_rows = hi - lo, r1 - r0
 
         def step():
@@ -304,6 +308,15 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     value = nnz * K_LAYERS / (ms_step * 1e-3) / 1e9
     launches_timed = _capi.launch_count() - launches0
+    phase_log = None
+    if prop is not None:   # one extra (untimed) step with per-phase CUDA events, max over ranks
+        prop.timing = []
+        step()
+        ph = prop.phase_ms()
+        prop.timing = None
+        tl = torch.tensor([x for _, x in ph], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        phase_log = [[n, round(float(x), 3)] for (n, _), x in zip(ph, tl.tolist())]
     launches_per_step = launches_timed // max(args.warmup + args.steps, 1)
 
     # roofline of the dominant kernel (CSR SpMM), per launch = one layer over this rank's rows.
@@ -460,9 +473,11 @@ def run_ours(args):
                                    f"(nnz(A)={nnz}), D={D}, K={K_LAYERS} (BASELINE.json configs[3], scale {args.scale:g})",
                        "edges_definition": "nnz(A) = 2*|R| per layer", "l2": "inputs larger than L2 (no flush needed)"
                        if nnz * 8 > 200e6 else "inputs smaller than L2: timing is L2-warm",
-                       "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" if world > 1 else ""),
+                       "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" + (f" e0={args.e0_exchange}" if args.exchange == "push" else "")
+                                                                       if world > 1 else ""),
                        "graph_build_s": round(t_gen, 2), "hot_rows_kept_in_l2": n_hot,
-                       "balance_ms_per_rank": balance_log if world > 1 else None},
+                       "balance_ms_per_rank": balance_log if world > 1 else None,
+                       "phase_ms_max_over_ranks": phase_log},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
         }

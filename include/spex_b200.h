@@ -263,6 +263,10 @@ int spex_ngcf_epilogue_f32(const float* ego, const float* side, const float* W1,
  * into up to 8 peer tables (P2P stores over NVLink): SpMM and all-gather in one kernel.
  */
 int spex_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64_host);
+/* all-gather of this rank's E^(0) rows by P2P stores: src fp32 [n_rows, D] is stored at rows
+ * [out_row_offset, out_row_offset + n_rows) of each of the n_peers (<= 8) tables (own included). */
+int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                       float* const* peer_Y_host, int32_t n_peers, void* stream);
 int spex_ipc_open(const void* handle64_host, void** dev_ptr);
 int spex_ipc_close(void* dev_ptr);
 int spex_ipc_free(void* dev_ptr);

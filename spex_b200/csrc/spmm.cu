@@ -375,6 +375,31 @@ __global__ void copy_f4_kernel(const float4* __restrict__ src, float4* __restric
   for (; i < n4; i += stride) dst[i] = src[i];
 }
 
+// all-gather of one rank's row slice by P2P stores: every 16-byte element is read once and stored
+// into each peer's table (the own table is just one more destination).  Peer p of block b is
+// visited starting at (b + p) so that the ranks' stores spread over the NVSwitch ports.
+struct PeerTables {
+  float* peer[8];
+  int n_peers;
+};
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const float4* __restrict__ src, int64_t n4, int64_t dst_off4, PeerTables pt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int rot = blockIdx.x % pt.n_peers;
+  for (; i < n4; i += stride) {
+    const float4 v = ld_stream_f4(reinterpret_cast<const float*>(src + i));
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if (p < pt.n_peers) {
+        int q = p + rot;
+        if (q >= pt.n_peers) q -= pt.n_peers;
+        reinterpret_cast<float4*>(pt.peer[q])[dst_off4 + i] = v;
+      }
+    }
+  }
+}
+
 __global__ void gather_scale_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                     const float* __restrict__ scale, float divisor,
                                     float* __restrict__ out, int64_t n) {
@@ -427,6 +452,25 @@ extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col,
     ep.peer[p] = peer_Y_host[p];
   }
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+extern "C" int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                  float* const* peer_Y_host, int32_t n_peers, void* stream) {
+  SPEX_RETURN_IF(!src || n_rows < 0 || out_row_offset < 0 || !peer_Y_host, SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_peers < 1 || n_peers > 8, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3), SPEX_E_BADDIM);
+  SPEX_RETURN_IF(!aligned16(src), SPEX_E_ALIGN);
+  PeerTables pt{};
+  pt.n_peers = n_peers;
+  for (int p = 0; p < n_peers; ++p) {
+    SPEX_RETURN_IF(!peer_Y_host[p] || !aligned16(peer_Y_host[p]), SPEX_E_BADARG);
+    pt.peer[p] = peer_Y_host[p];
+  }
+  if (n_rows == 0) return 0;
+  const int64_t n4 = n_rows * D / 4;
+  push_rows_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n4, out_row_offset * D / 4, pt);
+  count_launch();
+  return check_last();
 }
 
 extern "C" int spex_propagate_mean_f32(const int64_t* rowptr, const int32_t* col, const float* val,

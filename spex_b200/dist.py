@@ -14,6 +14,7 @@ Two exchange modes:
   "push"  the SpMM epilogue itself stores every output row into all peers' next-layer tables with
           P2P stores over NVLink (spex_spmm_csr_f32_push): transfer overlaps the gather-bound
           math row by row; layers are separated by a stream-ordered 4-byte all-reduce (barrier).
+          E^(0) travels the same way (spex_push_rows_f32: one read, P stores per element).
 
 The local multiply is injectable (``local_spmm``) so the orchestration can be tested on CPU with the
 oracle's SpMM under the gloo backend; the default is the CUDA kernel and there is no fallback.
@@ -62,6 +63,8 @@ class PartitionedPropagator:
         self._peer_ptrs = None
         self._raw = []
         self._flag = None
+        self.e0_exchange = "push" if mode == "push" else "nccl"   # "nccl" also allowed in push mode
+        self.timing = None        # set to [] to collect per-phase CUDA-event pairs (bring-up)
         if mode == "push":
             if local_spmm is not None:
                 raise ValueError("push mode is CUDA-only")
@@ -154,6 +157,29 @@ class PartitionedPropagator:
              self.g.n_rows, self.D, self.r0, self._peer_ptrs[push_buf], self.world,
              ptr(addend), 1.0, ptr(Z_local), float(z_scale), self.g.plan(self.D), stream_ptr())
 
+    def _mark(self, name):
+        if self.timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timing.append((name, ev))
+
+    def phase_ms(self):
+        """[(phase, ms)] between consecutive marks of the last propagate() (timing enabled)."""
+        torch.cuda.synchronize()
+        t = self.timing or []
+        return [(t[i + 1][0], t[i][1].elapsed_time(t[i + 1][1])) for i in range(len(t) - 1)]
+
+    def _exchange_e0(self, E0_local):
+        if self.mode == "push" and self.e0_exchange == "push":
+            from ._capi import call, ptr, stream_ptr
+
+            # everybody must be done reading buffer 0 (layer K-1 or K-2 of the previous call)
+            self._stream_barrier()
+            call("spex_push_rows_f32", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
+                 self._peer_ptrs[0], self.world, stream_ptr())
+        else:
+            self._all_gather_rows(self._X[0], E0_local)
+
     def propagate(self, E0_local: torch.Tensor) -> torch.Tensor:
         """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]."""
         K = self.K
@@ -162,9 +188,14 @@ class PartitionedPropagator:
             out.copy_(E0_local)
             return out
         inv = 1.0 / (K + 1)
-        self._all_gather_rows(self._X[0], E0_local)
+        if self.timing is not None:
+            self.timing = []
+        self._mark("start")
+        self._exchange_e0(E0_local)
+        self._mark("e0_exchange")
         if self.mode == "push":
-            self._stream_barrier()  # nobody may still be reading buffer 1 from a previous call
+            self._stream_barrier()  # E^(0) complete everywhere; nobody still reads buffer 1
+        self._mark("barrier")
         Y = None
         for k in range(K):
             last = k == K - 1
@@ -173,12 +204,16 @@ class PartitionedPropagator:
             if self.mode == "push":
                 self._layer(X_full, None, addend, out, inv if last else 1.0,
                             push_buf=None if last else (k + 1) & 1)
+                self._mark(f"layer{k + 1}")
                 if not last:
                     self._stream_barrier()
+                    self._mark("barrier")
             else:
                 if not last and Y is None:
                     Y = torch.empty_like(E0_local)
                 self._layer(X_full, None if last else Y, addend, out, inv if last else 1.0)
+                self._mark(f"layer{k + 1}")
                 if not last:
                     self._all_gather_rows(self._X[(k + 1) & 1], Y)
+                    self._mark("all_gather")
         return out
