@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10M x 5M x 1B workload")
     ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "push"), choices=["nccl", "push"])
-    ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE", "push"), choices=["nccl", "push"],
+    ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE", "nccl"), choices=["nccl", "push", "copy"],
                     help="how E^(0) is all-gathered in push mode")
     ap.add_argument("--eval-users", type=int, default=148 * 2 * 128)
     ap.add_argument("--no-eval", action="store_true")
@@ -261,16 +261,41 @@ def run_ours(args):
             if it == 2:
                 break
             y = torch.empty(r1 - r0, D, dtype=torch.float32, device=dev)
+            tprop = None
+            if args.exchange == "push":
+                # time the real thing: the layer kernel WITH its P2P stores into every peer's table
+                # (a rank with many short rows is bound by NVLink egress, not by the gathers)
+                tprop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode="push", device=dev)
+                tprop._all_gather_rows(tprop._X[0], table[r0:r1])
+                tprop._stream_barrier()
+                add = table[r0:r1]
+
+                def one():
+                    tprop._layer(tprop._X[0], None, add, y, 1.0, push_buf=1)
+            else:
+                def one():
+                    ops.spmm(lg, table, Y=y)
             for _ in range(2):
-                ops.spmm(lg, table, Y=y)
+                one()
+                if tprop is not None:
+                    tprop._stream_barrier()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            if world > 1:
+                dist.barrier()
+            ms_sum = 0.0
             for _ in range(3):
-                ops.spmm(lg, table, Y=y)
-            e1.record()
-            torch.cuda.synchronize()
-            tl = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                one()
+                e1.record()
+                if tprop is not None:
+                    tprop._stream_barrier()   # all ranks run the layer at the same time
+                torch.cuda.synchronize()
+                ms_sum += e0.elapsed_time(e1)
+            if tprop is not None:
+                tprop.close()
+                del tprop
+            tl = torch.tensor([ms_sum / 3], dtype=torch.float64, device=dev)
             allt = [torch.zeros_like(tl) for _ in range(world)]
             dist.all_gather(allt, tl)
             times = [float(x.item()) for x in allt]

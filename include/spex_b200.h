@@ -270,6 +270,9 @@ int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_
 int spex_ipc_open(const void* handle64_host, void** dev_ptr);
 int spex_ipc_close(void* dev_ptr);
 int spex_ipc_free(void* dev_ptr);
+/* cudaMemcpyAsync(DeviceToDevice) on `stream`: a copy-engine transfer into an IPC-mapped peer
+ * table (dst may be peer memory), used for the E^(0) all-gather so that no SM is involved. */
+int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream);
 int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,
                            const float* X, int64_t n_rows, int32_t D,
                            int64_t out_row_offset, float* const* peer_Y_host, int32_t n_peers,

@@ -146,3 +146,10 @@ extern "C" int spex_ipc_free(void* dev_ptr) {
   SPEX_RETURN_IF(!dev_ptr, SPEX_E_BADARG);
   return (int)cudaFree(dev_ptr);
 }
+
+// copy-engine transfer into an IPC-mapped peer table (E^(0) all-gather without using any SM)
+extern "C" int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  SPEX_RETURN_IF(!dst || !src || bytes < 0, SPEX_E_BADARG);
+  if (bytes == 0) return 0;
+  return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}

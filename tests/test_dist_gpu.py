@@ -49,7 +49,7 @@ def _worker(rank, world, port, q):
         lg = ops.DeviceGraph((full.rowptr[r0: r1 + 1] - lo).contiguous(), full.col[lo:hi].clone(),
                              full.val[lo:hi].clone(), N, None, full.seg_len, row_offset=r0)
         res = {}
-        for mode, e0 in (("nccl", "nccl"), ("push", "push"), ("push", "nccl")):
+        for mode, e0 in (("nccl", "nccl"), ("push", "push"), ("push", "copy"), ("push", "nccl")):
             prop = PartitionedPropagator(lg, bounds, D, K, mode=mode, device=dev)
             prop.e0_exchange = e0
             a = prop.propagate(E[r0:r1].clone())
