@@ -333,6 +333,25 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     value = nnz * K_LAYERS / (ms_step * 1e-3) / 1e9
     launches_timed = _capi.launch_count() - launches0
+    # parity at full size, untimed: D^-1/2 A D^-1/2 has the eigenvector sqrt(deg) (eigenvalue 1), so
+    # propagating a table whose columns are multiples of sqrt(deg) must return it unchanged
+    gsrc = g if world == 1 else lg
+    deg = (gsrc.rowptr[1:] - gsrc.rowptr[:-1]).to(torch.float32)
+    Echk = deg.sqrt()[:, None] * (1.0 + torch.arange(D, device=dev, dtype=torch.float32) / D)[None, :]
+    if world == 1:
+        ochk = torch.empty_like(Echk)
+        _capi.call("spex_propagate_mean_f32", _capi.ptr(g.rowptr), _capi.ptr(g.col), _capi.ptr(g.val),
+                   _capi.ptr(Echk), N, D, K_LAYERS, _capi.ptr(ochk), _capi.ptr(tmp0), _capi.ptr(tmp1),
+                   g.plan(D), _capi.stream_ptr())
+    else:
+        ochk = prop.propagate(Echk)
+    nzr = deg > 0
+    relerr = ((ochk[nzr] - Echk[nzr]).abs() / Echk[nzr]).max().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(relerr, op=dist.ReduceOp.MAX)
+    parity = {"check": "sqrt(deg) is a fixed point of every layer and of the layer mean (all edges, all ranks)",
+              "max_rel_err": float(relerr.item()), "tolerance": 1e-5, "ok": bool(float(relerr.item()) < 1e-5)}
+    del Echk, ochk, deg, nzr
     phase_log = None
     if prop is not None:   # one extra (untimed) step with per-phase CUDA events, max over ranks
         prop.timing = []
@@ -503,7 +522,7 @@ def run_ours(args):
                        "graph_build_s": round(t_gen, 2), "hot_rows_kept_in_l2": n_hot,
                        "balance_ms_per_rank": balance_log if world > 1 else None,
                        "phase_ms_max_over_ranks": phase_log},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "parity": parity,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
         }
         print(json.dumps(line), flush=True)
