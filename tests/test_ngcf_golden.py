@@ -1,0 +1,120 @@
+"""BASELINE.json configs[2] - NGCF_SPEX propagation (SpMM with D^-1(A+I) + per-layer dense W1/W2
+epilogue) - against golden vectors produced by the unmodified reference
+(tests/golden/make_ngcf.py: /root/reference/NGCF_SPEX/code/main_rec.py::Model_Wrapper and
+utility/load_data.py::Data.create_adj_mat on the reference-processed epinion2 data)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import lightgcn_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def seeded_ngcf_weights(n_user_rows, n_items, D=64, seed=11):
+    """Same numpy stream as tests/golden/make_ngcf.py::seeded_ngcf_weights."""
+    rng = np.random.default_rng(seed)
+    au, ai, aw = np.sqrt(6.0 / (n_user_rows + D)), np.sqrt(6.0 / (n_items + D)), 1.0 / np.sqrt(D)
+    return {
+        "user": rng.uniform(-au, au, (n_user_rows, D)).astype(np.float32),
+        "item": rng.uniform(-ai, ai, (n_items, D)).astype(np.float32),
+        "W1": rng.uniform(-aw, aw, (D, D)).astype(np.float32), "b1": rng.uniform(-aw, aw, D).astype(np.float32),
+        "W2": rng.uniform(-aw, aw, (D, D)).astype(np.float32), "b2": rng.uniform(-aw, aw, D).astype(np.float32),
+    }
+
+
+@pytest.fixture(scope="module")
+def G():
+    return dict(np.load(os.path.join(GOLD, "ngcf_epinion2.npz")))
+
+
+@pytest.fixture(scope="module")
+def data():
+    return np.load(os.path.join(GOLD, "epinion2_data.npz"))
+
+
+@pytest.fixture(scope="module")
+def graph(G, data):
+    from spex_b200.ngcf import build_ngcf_norm_adj
+
+    return build_ngcf_norm_adj(data["train_user"], data["train_item"], int(G["n_users"]), int(G["n_items"]))
+
+
+def test_ngcf_adjacency_matches_reference(G, data, graph):
+    u, i = data["train_user"].astype(np.int64), data["train_item"].astype(np.int64)
+    # NGCF's train.txt holds the same interactions, with the same ids, as LightGCN's files
+    assert u.size == int(G["n_train"]) and int((u * 1000003 + i).sum()) == int(G["train_pairs_checksum"])
+    assert graph.nnz == int(G["adj_nnz"]) == 434200
+    rows = graph.rows_of_entries()
+    pick = G["adj_pick"]
+    assert np.array_equal(np.stack([rows[pick], graph.col[pick].astype(np.int64)]), G["adj_pick_rc"])
+    assert np.array_equal(graph.val[pick], G["adj_pick_val"]), "values must be bit-equal"
+    assert float(graph.val.astype(np.float64).sum()) == float(G["adj_value_sum"])
+    # row sums are 1 and the matrix is NOT symmetric (load_data.py:162)
+    rs = np.bincount(rows, weights=graph.val.astype(np.float64), minlength=graph.n_rows)
+    assert np.allclose(rs, 1.0, atol=1e-6)
+    assert not np.array_equal(graph.val, graph.val[graph.tpos])
+    assert np.array_equal(rows[graph.tpos], graph.col) and np.array_equal(graph.col[graph.tpos], rows)
+
+
+def test_oracle_ngcf_forward(G, graph):
+    nu, ni = int(G["n_users"]), int(G["n_items"])
+    W = {k: torch.from_numpy(v) for k, v in seeded_ngcf_weights(nu + 1, ni).items()}
+    A = torch.sparse_coo_tensor(torch.from_numpy(np.stack([graph.rows_of_entries(), graph.col.astype(np.int64)])),
+                                torch.from_numpy(graph.val), (graph.n_rows, graph.n_cols)).coalesce()
+    ego = torch.cat([W["user"][:-1], W["item"]])
+    _, norm = O.ngcf_layer(A, ego, W["W1"], W["b1"], W["W2"], W["b2"], 0.01)
+    out = torch.cat([ego, norm], dim=1).numpy()
+    assert np.allclose(out[::29], G["out_rows_29"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(out.astype(np.float64).sum(0), G["out_colsum"], rtol=1e-5, atol=1e-4)
+
+
+def _model(G, graph, dev):
+    from spex_b200.ngcf import Model_Wrapper
+
+    nu, ni = int(G["n_users"]), int(G["n_items"])
+    model = Model_Wrapper({"n_users": nu, "n_items": ni, "norm_adj": graph}, dev)
+    W = seeded_ngcf_weights(nu + 1, ni)
+    with torch.no_grad():
+        model.user_embedding.weight.copy_(torch.from_numpy(W["user"]))
+        model.item_embedding.weight.copy_(torch.from_numpy(W["item"]))
+        model.GC_Linear_list[0].weight.copy_(torch.from_numpy(W["W1"]))
+        model.GC_Linear_list[0].bias.copy_(torch.from_numpy(W["b1"]))
+        model.Bi_Linear_list[0].weight.copy_(torch.from_numpy(W["W2"]))
+        model.Bi_Linear_list[0].bias.copy_(torch.from_numpy(W["b2"]))
+    return model.to(dev)
+
+
+@pytest.mark.gpu
+def test_gpu_ngcf_forward_fused_and_differentiable(G, graph, cuda_device):
+    model = _model(G, graph, cuda_device)
+    model.eval()
+    with torch.no_grad():
+        ua, ia = model(None, None, None, 1)                   # fused epilogue kernel
+    assert ua.shape == (int(G["n_users"]), 128) and ia.shape == (int(G["n_items"]), 128)
+    rows = torch.cat([ua, ia]).cpu()
+    assert rel_err(rows[::29], torch.from_numpy(G["out_rows_29"])) < 1e-5
+    assert np.allclose(rows.double().sum(0).numpy(), G["out_colsum"], rtol=1e-5, atol=1e-4)
+    ua2, ia2 = model(None, None, None, 1)                     # autograd composition, same numbers
+    assert rel_err(torch.cat([ua2, ia2]).detach().cpu(), rows) < 1e-5
+    users = torch.arange(0, 64, device=cuda_device)
+    scores = model.rate_all_items(users)                      # utility/batch_test.py:158
+    assert rel_err(scores, ua[users] @ ia.t()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_ngcf_loss_and_gradients(G, graph, cuda_device):
+    model = _model(G, graph, cuda_device)
+    model.eval()                                              # golden was taken without dropout
+    model.zero_grad()
+    loss = model(G["batch_users"], G["batch_items"], G["batch_labels"], 0)
+    loss.backward()
+    assert abs(float(loss) - float(G["bce_loss"])) < 1e-5 * float(G["bce_loss"])
+    for name, got in (("grad_W1", model.GC_Linear_list[0].weight.grad), ("grad_W2", model.Bi_Linear_list[0].weight.grad),
+                      ("grad_b1", model.GC_Linear_list[0].bias.grad), ("grad_b2", model.Bi_Linear_list[0].bias.grad)):
+        assert rel_err(got.cpu(), torch.from_numpy(G[name])) < 1e-4, name
+    assert rel_err(model.user_embedding.weight.grad.cpu()[::29], torch.from_numpy(G["grad_user_rows_29"])) < 1e-4
+    assert rel_err(model.item_embedding.weight.grad.cpu()[::29], torch.from_numpy(G["grad_item_rows_29"])) < 1e-4
