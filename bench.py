@@ -45,9 +45,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10M x 5M x 1B workload")
-    ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "push"), choices=["nccl", "push"])
-    ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE", "nccl"), choices=["nccl", "push", "copy"],
-                    help="how E^(0) is all-gathered in push mode")
+    ap.add_argument("--exchange", default=os.environ.get("SPEX_EXCHANGE", "auto"),
+                    choices=["auto", "nccl", "push", "mcast"],
+                    help="auto = mcast (NVLS multicast stores) when the box supports it, else push")
+    ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE"), choices=["nccl", "push", "copy", "mcast"],
+                    help="how E^(0) is all-gathered in push / mcast mode")
     ap.add_argument("--eval-users", type=int, default=148 * 2 * 128)
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,20 +254,30 @@ def run_ours(args):
         # set-up (untimed): equalise the MEASURED local SpMM time of the ranks.  Blocks of user rows
         # (popular item rows hit L2) and of item rows (random user rows do not) cost differently
         # per edge, so a pure nnz balance leaves the item-row ranks as stragglers.
+        if args.exchange == "auto":   # NVLS multicast needs NVSwitch + driver support: probe once
+            try:
+                probe = PartitionedPropagator(None, [0] * world + [16], D, K_LAYERS, mode="mcast", device=dev)
+                probe.close()
+                ok = torch.ones(1, device=dev)
+            except Exception:
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            args.exchange = "mcast" if float(ok.item()) > 0 else "push"
         balance_log = []
-        for it in range(3):
+        n_bal = 4
+        for it in range(n_bal):
             r0, r1 = bounds[rank], bounds[rank + 1]
             lo, hi = int(rp_host[r0]), int(rp_host[r1])
             lg = ops.DeviceGraph((g.rowptr[r0: r1 + 1] - lo).contiguous(), g.col[lo:hi], g.val[lo:hi], N,
                                  None, g.seg_len, row_offset=r0, col_hot=g.col_hot)
-            if it == 2:
+            if it == n_bal - 1:
                 break
             y = torch.empty(r1 - r0, D, dtype=torch.float32, device=dev)
             tprop = None
-            if args.exchange == "push":
+            if args.exchange in ("push", "mcast"):
                 # time the real thing: the layer kernel WITH its P2P stores into every peer's table
                 # (a rank with many short rows is bound by NVLink egress, not by the gathers)
-                tprop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode="push", device=dev)
+                tprop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
                 tprop._all_gather_rows(tprop._X[0], table[r0:r1])
                 tprop._stream_barrier()
                 add = table[r0:r1]
@@ -308,8 +320,8 @@ def run_ours(args):
         del g, table
         torch.cuda.empty_cache()
         prop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
-        if args.exchange == "push":
-            prop.e0_exchange = args.e0_exchange
+        if args.e0_exchange is not None and args.exchange != "nccl":
+            prop.e0_exchange = args.e0_exchange   # default: nccl in push mode, mcast in mcast mode
         local_nnz, local_rows = hi - lo, r1 - r0
 
         def step():
@@ -517,7 +529,7 @@ def run_ours(args):
                                    f"(nnz(A)={nnz}), D={D}, K={K_LAYERS} (BASELINE.json configs[3], scale {args.scale:g})",
                        "edges_definition": "nnz(A) = 2*|R| per layer", "l2": "inputs larger than L2 (no flush needed)"
                        if nnz * 8 > 200e6 else "inputs smaller than L2: timing is L2-warm",
-                       "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" + (f" e0={args.e0_exchange}" if args.exchange == "push" else "")
+                       "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" + (f" e0={prop.e0_exchange}" if args.exchange != "nccl" else "")
                                                                        if world > 1 else ""),
                        "graph_build_s": round(t_gen, 2), "hot_rows_kept_in_l2": n_hot,
                        "balance_ms_per_rank": balance_log if world > 1 else None,

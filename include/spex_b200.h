@@ -270,6 +270,15 @@ int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_
 int spex_ipc_open(const void* handle64_host, void** dev_ptr);
 int spex_ipc_close(void* dev_ptr);
 int spex_ipc_free(void* dev_ptr);
+/* NVLS variants: `mcast_Y` is the NVSwitch multicast mapping (cuMulticast*, e.g. torch symmetric
+ * memory's multicast_ptr) of the peers' tables; every output row / E^(0) element is stored ONCE with
+ * multimem.st and the switch replicates it into all GPUs' copies (own included). */
+int spex_spmm_csr_f32_mcast(const int64_t* rowptr, const int32_t* col, const float* val,
+                            const float* X, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                            float* mcast_Y, const float* addend, float addend_scale, float* Z,
+                            float z_scale, const spex_long_plan* plan, void* stream);
+int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                        float* mcast_Y, void* stream);
 /* cudaMemcpyAsync(DeviceToDevice) on `stream`: a copy-engine transfer into an IPC-mapped peer
  * table (dst may be peer memory), used for the E^(0) all-gather so that no SM is involved. */
 int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream);

@@ -66,6 +66,13 @@ __device__ __forceinline__ float4 ld_gather_f4_hint(const float* p, uint64_t pol
       : "l"(p), "l"(policy));
   return v;
 }
+// 128-bit store to an NVSwitch multicast address (cuMulticast mapping of the same buffer on every
+// GPU of the group): the switch delivers it to all of them.
+__device__ __forceinline__ void st_multimem_f4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 // plain (coherent) 128-bit load: for buffers that the same kernel also writes (in-place Z).
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   return *reinterpret_cast<const float4*>(p);

@@ -110,6 +110,9 @@ struct Epilogue {
   float* peer[8];
   int n_peers;
   int64_t peer_row_offset;
+  // or ONE store to an NVSwitch multicast mapping of the peers' tables (NVLS): the switch
+  // replicates it into every GPU's copy, so the row leaves this GPU once instead of P-1 times
+  float* mcast;
 };
 
 template <int D>
@@ -118,7 +121,9 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
   if (lane < LPR) {
     const int64_t off = row * D + lane * 4;
     if (ep.Y) *reinterpret_cast<float4*>(ep.Y + off) = acc;
-    if (ep.n_peers > 0) {
+    if (ep.mcast) {
+      st_multimem_f4(ep.mcast + (row + ep.peer_row_offset) * D + lane * 4, acc);
+    } else if (ep.n_peers > 0) {
       const int64_t poff = (row + ep.peer_row_offset) * D + lane * 4;
 #pragma unroll
       for (int p = 0; p < 8; ++p)
@@ -400,6 +405,15 @@ push_rows_kernel(const float4* __restrict__ src, int64_t n4, int64_t dst_off4, P
   }
 }
 
+// the same all-gather with ONE multicast store per element (NVLS)
+__global__ void __launch_bounds__(256)
+mcast_rows_kernel(const float4* __restrict__ src, int64_t n4, float* __restrict__ mcast_dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride)
+    st_multimem_f4(mcast_dst + 4 * i, ld_stream_f4(reinterpret_cast<const float*>(src + i)));
+}
+
 __global__ void gather_scale_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                     const float* __restrict__ scale, float divisor,
                                     float* __restrict__ out, int64_t n) {
@@ -452,6 +466,34 @@ extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col,
     ep.peer[p] = peer_Y_host[p];
   }
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+extern "C" int spex_spmm_csr_f32_mcast(const int64_t* rowptr, const int32_t* col, const float* val,
+                                       const float* X, int64_t n_rows, int32_t D,
+                                       int64_t out_row_offset, float* mcast_Y, const float* addend,
+                                       float addend_scale, float* Z, float z_scale,
+                                       const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(!mcast_Y || !aligned16(mcast_Y) || out_row_offset < 0, SPEX_E_BADARG);
+  Epilogue ep{};
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.peer_row_offset = out_row_offset;
+  ep.mcast = mcast_Y;
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+extern "C" int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                   float* mcast_Y, void* stream) {
+  SPEX_RETURN_IF(!src || !mcast_Y || n_rows < 0 || out_row_offset < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(D <= 0 || (D & 3), SPEX_E_BADDIM);
+  SPEX_RETURN_IF(!aligned16(src) || !aligned16(mcast_Y), SPEX_E_ALIGN);
+  if (n_rows == 0) return 0;
+  mcast_rows_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n_rows * D / 4,
+                                                               mcast_Y + out_row_offset * D);
+  count_launch();
+  return check_last();
 }
 
 extern "C" int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,

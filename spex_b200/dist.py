@@ -9,13 +9,18 @@ is that partition with one process per GPU: rank p owns the contiguous node rang
     1. assembles the full E^(k) [N, D] on every rank (the exchange),
     2. runs the local CSR SpMM over its rows, accumulating the layer mean in its own slice.
 
-Two exchange modes:
+Three exchange modes:
   "nccl"  one all-gather of the [rows_p, D] slices per layer (torch.distributed over NCCL/NVLink);
   "push"  the SpMM epilogue itself stores every output row into all peers' next-layer tables with
           P2P stores over NVLink (spex_spmm_csr_f32_push): transfer overlaps the gather-bound
           math row by row; layers are separated by a stream-ordered 4-byte all-reduce (barrier).
           E^(0) has no producing kernel to fuse with and travels by NCCL all-gather (measured
           faster than P2P stores or copy engines, which stay selectable: e0_exchange).
+
+  "mcast" the same fusion with ONE store per row to an NVSwitch multicast mapping of the tables
+          (NVLS; torch symmetric memory provides the mapping): a row leaves the GPU once instead of
+          P-1 times, which removes the NVLink egress bound of "push" (spex_spmm_csr_f32_mcast,
+          spex_mcast_rows_f32 for E^(0)).
 
 The local multiply is injectable (``local_spmm``) so the orchestration can be tested on CPU with the
 oracle's SpMM under the gloo backend; the default is the CUDA kernel and there is no fallback.
@@ -70,15 +75,22 @@ class PartitionedPropagator:
         self.e0_exchange = "nccl"
         self._copy_streams = []
         self.timing = None        # set to [] to collect per-phase CUDA-event pairs (bring-up)
+        self._mc = None           # multicast pointers of the two tables (mode "mcast")
+        self._symm = []
         if mode == "push":
             if local_spmm is not None:
                 raise ValueError("push mode is CUDA-only")
             self._setup_push()
+        elif mode == "mcast":
+            if local_spmm is not None:
+                raise ValueError("mcast mode is CUDA-only")
+            self._setup_mcast()
+            self.e0_exchange = "mcast"
         elif mode == "nccl":
             self._X = [torch.empty(self.N, self.D, dtype=torch.float32, device=self.device)
                        for _ in range(2 if self.K > 1 else 1)]
         else:
-            raise ValueError("mode must be 'nccl' or 'push'")
+            raise ValueError("mode must be 'nccl', 'push' or 'mcast'")
 
     # ---- push mode: IPC-mapped double-buffered tables --------------------------------------------
     def _setup_push(self):
@@ -111,7 +123,28 @@ class PartitionedPropagator:
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         dist.barrier(group=self.group)
 
+    # ---- mcast mode: symmetric-memory tables with an NVSwitch multicast mapping -------------------
+    def _setup_mcast(self):
+        import torch.distributed._symmetric_memory as symm
+
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._mc = []
+        for _ in range(2):
+            t = symm.empty(self.N * self.D, dtype=torch.float32, device=self.device)
+            h = symm.rendezvous(t, group)
+            if not h.multicast_ptr:
+                raise RuntimeError("this box has no NVLS multicast support: use mode='push'")
+            self._symm.append((t, h))
+            self._X.append(t.view(self.N, self.D))
+            self._mc.append(int(h.multicast_ptr))
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=self.group)
+
     def close(self):
+        if self.mode == "mcast" and self._symm:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            self._X, self._symm, self._mc = [], [], None
         if self.mode == "push" and self._raw:
             from ._capi import call
 
@@ -157,6 +190,11 @@ class PartitionedPropagator:
         if push_buf is None:
             ops.spmm(self.g, X_full, Y=Y_local, addend=addend, addend_scale=1.0, Z=Z_local, z_scale=z_scale)
             return
+        if self.mode == "mcast":   # fused SpMM + all-gather, one multicast store per row
+            call("spex_spmm_csr_f32_mcast", ptr(self.g.rowptr), ptr(self.g.col), ptr(self.g.val), ptr(X_full),
+                 self.g.n_rows, self.D, self.r0, C.c_void_p(self._mc[push_buf]),
+                 ptr(addend), 1.0, ptr(Z_local), float(z_scale), self.g.plan(self.D), stream_ptr())
+            return
         # fused SpMM + all-gather: rows go to every peer's (and our own) next-layer table
         call("spex_spmm_csr_f32_push", ptr(self.g.rowptr), ptr(self.g.col), ptr(self.g.val), ptr(X_full),
              self.g.n_rows, self.D, self.r0, self._peer_ptrs[push_buf], self.world,
@@ -175,7 +213,13 @@ class PartitionedPropagator:
         return [(t[i + 1][0], t[i][1].elapsed_time(t[i + 1][1])) for i in range(len(t) - 1)]
 
     def _exchange_e0(self, E0_local):
-        if self.mode == "push" and self.e0_exchange in ("push", "copy"):
+        if self.mode == "mcast" and self.e0_exchange == "mcast":
+            from ._capi import call, ptr, stream_ptr
+
+            self._stream_barrier()   # everybody is done reading buffer 0 from the previous call
+            call("spex_mcast_rows_f32", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
+                 C.c_void_p(self._mc[0]), stream_ptr())
+        elif self.mode == "push" and self.e0_exchange in ("push", "copy"):
             from ._capi import call, ptr, stream_ptr
 
             # everybody must be done reading buffer 0 (layer K-1 or K-2 of the previous call)
@@ -222,7 +266,7 @@ class PartitionedPropagator:
         self._mark("start")
         self._exchange_e0(E0_local)
         self._mark("e0_exchange")
-        if self.mode == "push":
+        if self.mode in ("push", "mcast"):
             self._stream_barrier()  # E^(0) complete everywhere; nobody still reads buffer 1
         self._mark("barrier")
         Y = None
@@ -230,7 +274,7 @@ class PartitionedPropagator:
             last = k == K - 1
             X_full = self._X[k & 1]
             addend = E0_local if k == 0 else out
-            if self.mode == "push":
+            if self.mode in ("push", "mcast"):
                 self._layer(X_full, None, addend, out, inv if last else 1.0,
                             push_buf=None if last else (k + 1) & 1)
                 self._mark(f"layer{k + 1}")

@@ -49,7 +49,14 @@ def _worker(rank, world, port, q):
         lg = ops.DeviceGraph((full.rowptr[r0: r1 + 1] - lo).contiguous(), full.col[lo:hi].clone(),
                              full.val[lo:hi].clone(), N, None, full.seg_len, row_offset=r0)
         res = {}
-        for mode, e0 in (("nccl", "nccl"), ("push", "push"), ("push", "copy"), ("push", "nccl")):
+        modes = [("nccl", "nccl"), ("push", "push"), ("push", "copy"), ("push", "nccl")]
+        try:   # NVLS multicast needs an NVSwitch box
+            probe = PartitionedPropagator(lg, bounds, D, K, mode="mcast", device=dev)
+            probe.close()
+            modes += [("mcast", "mcast"), ("mcast", "nccl")]
+        except RuntimeError as e:
+            res["mcast_unavailable"] = (True, True, ["layer3", "e0_exchange", str(e)])
+        for mode, e0 in modes:
             prop = PartitionedPropagator(lg, bounds, D, K, mode=mode, device=dev)
             prop.e0_exchange = e0
             a = prop.propagate(E[r0:r1].clone())
