@@ -382,10 +382,10 @@ def run_ours(args):
     t_launch = ms_step * 1e-3 / K_LAYERS
     achieved = alg_bytes / t_launch / 1e9
     # DRAM traffic per layer from the round's `ncu --set full` capture of this exact workload
-    # (profiles/r01_ncu_spmm_final.json: rows 244.92+7.57, segments 126.53+0.52, fix 0.60+0.02 GB):
-    # 380.2 GB, i.e. 0.72 of the algorithmic bytes - L2 re-use of popular item rows, no re-reads.
-    traffic = 380.16e9 if (world == 1 and args.scale == 1.0) else None
-    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8> + spmm_seg_list_kernel<64,8> + "
+    # (profiles/r01_ncu_spmm_final.json: rows 164.73+7.58, segments 121.50+0.53, fix 0.60+0.02 GB):
+    # 295.0 GB, i.e. 0.55 of the algorithmic bytes - L2 re-use of popular item rows, no re-reads.
+    traffic = 294.96e9 if (world == 1 and args.scale == 1.0) else None
+    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8,1> + spmm_seg_list_kernel<64,8,1> + "
                                           "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
@@ -503,7 +503,7 @@ def run_ours(args):
                  "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": tf,
                               "peak": tc_burst, "unit": "TFLOP/s", "frac": tf / tc_burst,
                               "peak_kind": peak_kind,
-                              "traffic": 761.8e6 if (world == 1 and args.scale == 1.0 and
+                              "traffic": 861.8e6 if (world == 1 and args.scale == 1.0 and
                                                      n_eval == 148 * 2 * 128) else None}}
 
     launches_total = _capi.launch_count() - launches0
