@@ -179,8 +179,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ge, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cpu sample of synthetic 10M users x 5M items, 1B interactions, D=64, K=3",
-                   "sample": sample},
+        "config": {"workload": f"synthetic {G_USERS} users x {G_ITEMS} items, {G_INTER} interactions, D={D}, "
+                               f"K={K_LAYERS} (BASELINE.json configs[3]) - timed on a bounded sample of it",
+                   "sample": sample, "parallelism": f"{cores} host threads (torch.sparse.mm)"},
         "cpu_baseline": {"value": ge, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ge, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
