@@ -18,6 +18,8 @@ There is no CPU fallback: every op raises on a CPU tensor.
 """
 from __future__ import annotations
 
+import ast
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -99,12 +101,12 @@ class Model_Wrapper(nn.Module):
         g = lambda name, default: getattr(args, name, default) if args is not None else default  # noqa: E731
         self.embedding_dim = int(g("embed_size", 64))
         layer_size = g("layer_size", "[64]")
-        self.weight_size = list(eval(layer_size)) if isinstance(layer_size, str) else list(layer_size)
+        self.weight_size = list(ast.literal_eval(layer_size)) if isinstance(layer_size, str) else list(layer_size)
         self.n_layers = len(self.weight_size)
         mess = g("mess_dropout", "[0.1]")
-        self.mess_dropout = list(eval(mess)) if isinstance(mess, str) else list(mess)
+        self.mess_dropout = list(ast.literal_eval(mess)) if isinstance(mess, str) else list(mess)
         regs = g("regs", "[1e-5]")
-        self.regs = list(eval(regs)) if isinstance(regs, str) else list(regs)
+        self.regs = list(ast.literal_eval(regs)) if isinstance(regs, str) else list(regs)
         self.decay = self.regs[0]
         self.negative_slope = 0.01                      # F.leaky_relu default (main_rec.py:77,79)
         if any(w != self.embedding_dim for w in self.weight_size) or self.embedding_dim != 64:

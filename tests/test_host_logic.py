@@ -225,3 +225,36 @@ def test_epoch_batches_follow_dataloader_shuffle():
     mine, mine2 = epoch_batches(1000, 256), epoch_batches(1000, 256)
     assert all(torch.equal(a, b) for a, b in zip(ref, mine)) and len(ref) == len(mine)
     assert all(torch.equal(a, b) for a, b in zip(ref2, mine2))
+
+
+def test_ngcf_adjacency_builder_edge_cases():
+    """D^-1 (A + I) (NGCF_SPEX/code/utility/load_data.py:122-166): duplicates collapse (dok
+    assignment), isolated nodes keep their self loop with weight 1, rows sum to 1, and the scipy
+    hand-off used by Model_Wrapper(data_config['norm_adj']) round-trips."""
+    import scipy.sparse as sp
+
+    from spex_b200.ngcf import build_ngcf_norm_adj, csr_from_scipy
+
+    nu, ni = 5, 4
+    users = np.array([0, 0, 0, 2, 2, 4])
+    items = np.array([1, 1, 3, 0, 3, 3])          # (0,1) twice; user 1, user 3, item 2 isolated
+    g = build_ngcf_norm_adj(users, items, nu, ni)
+    A = sp.dok_matrix((nu + ni, nu + ni), dtype=np.float32)
+    for u, i in zip(users, items):
+        A[u, nu + i] = 1.0
+        A[nu + i, u] = 1.0
+    A = (A.tocsr() + sp.eye(nu + ni)).tocsr()
+    want = sp.diags(1.0 / np.asarray(A.sum(1)).ravel()).dot(A).tocsr().astype(np.float32)
+    want.sort_indices()
+    assert np.array_equal(g.rowptr, want.indptr) and np.array_equal(g.col, want.indices)
+    assert np.array_equal(g.val, want.data)
+    rows = g.rows_of_entries()
+    assert np.allclose(np.bincount(rows, weights=g.val, minlength=g.n_rows), 1.0)
+    for node in (1, 3, nu + 2):                     # isolated: only the self loop, weight 1
+        assert g.rowptr[node + 1] - g.rowptr[node] == 1 and g.val[g.rowptr[node]] == 1.0
+    assert np.array_equal(rows[g.tpos], g.col) and np.array_equal(g.col[g.tpos], rows)
+    h = csr_from_scipy(want)
+    assert np.array_equal(h.rowptr, g.rowptr) and np.array_equal(h.col, g.col) and np.array_equal(h.val, g.val)
+    assert np.array_equal(h.tpos, g.tpos)
+    with pytest.raises(ValueError):
+        build_ngcf_norm_adj(np.array([5]), np.array([0]), nu, ni)
