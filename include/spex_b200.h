@@ -58,6 +58,12 @@ int64_t spex_launch_count(void);
  * should stay in L2): the kernels strip the bit and gather hot rows with the L2 evict_last policy,
  * all others with evict_first.  A plan with n_long == 0 may still carry this flag. */
 #define SPEX_PLAN_COL_HOTBIT 1
+/* two-pass rows: inside every short row of [0, n_split_rows) the hot edges were moved to the
+ * front (rowmid[r] = first cold edge).  Pass A reduces only hot edges - its working set is the hot
+ * part of the table plus streamed (col, val), so it stays L2-resident by construction - into
+ * hot_partial; pass B reduces the cold edges (pure streaming) and adds the partial row.  Needs
+ * SPEX_PLAN_COL_HOTBIT. */
+#define SPEX_PLAN_TWO_PASS 2
 
 typedef struct spex_long_plan {
   int32_t seg_len;            /* rows with degree > seg_len take the long-row path (>= 32)    */
@@ -70,6 +76,9 @@ typedef struct spex_long_plan {
   const int64_t* seg_start;   /* int64 [n_seg]  first edge of each segment (NULL: fixed-length) */
   const int32_t* seg_count;   /* int32 [n_seg]  edges in each segment                         */
   const int32_t* row_seg;     /* int32 [n_seg]  segment ids grouped by long row, column order */
+  const int64_t* rowmid;      /* int64 [n_rows]  SPEX_PLAN_TWO_PASS: first cold edge of every row */
+  float* hot_partial;         /* fp32  [n_split_rows, D] workspace of pass A                   */
+  int64_t n_split_rows;       /* rows [0, n_split_rows) take part in pass A                    */
 } spex_long_plan;
 
 /*

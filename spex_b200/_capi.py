@@ -32,6 +32,9 @@ class LongPlan(C.Structure):
         ("seg_start", _p),
         ("seg_count", _p),
         ("row_seg", _p),
+        ("rowmid", _p),
+        ("hot_partial", _p),
+        ("n_split_rows", _i64),
     ]
 
 

@@ -113,6 +113,9 @@ struct Epilogue {
   // or ONE store to an NVSwitch multicast mapping of the peers' tables (NVLS): the switch
   // replicates it into every GPU's copy, so the row leaves this GPU once instead of P-1 times
   float* mcast;
+  // two-pass rows (SPEX_PLAN_TWO_PASS): partial row of the hot pass, added before anything else
+  const float* partial_in;
+  int64_t n_partial;
 };
 
 template <int D>
@@ -120,6 +123,7 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
   constexpr int LPR = RowShape<D>::LPR;
   if (lane < LPR) {
     const int64_t off = row * D + lane * 4;
+    if (ep.partial_in && row < ep.n_partial) f4_add(acc, ld_stream_f4(ep.partial_in + off));
     if (ep.Y) *reinterpret_cast<float4*>(ep.Y + off) = acc;
     if (ep.mcast) {
       st_multimem_f4(ep.mcast + (row + ep.peer_row_offset) * D + lane * 4, acc);
@@ -158,12 +162,15 @@ template <int D, int U, bool kHot>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
-                 int32_t skip_longer_than, Epilogue ep) {
+                 int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const int64_t start = rowptr[row], end = rowptr[row + 1];
+  int64_t start = rowptr[row], end = rowptr[row + 1];
   if (skip_longer_than > 0 && end - start > skip_longer_than) return;  // long-row path
+  // two-pass rows: pass 1 = hot edges [start, rowmid), pass 2 = cold edges [rowmid, end)
+  if (pass == 1) end = rowmid[row];
+  if (pass == 2) start = rowmid[row];
   const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
   row_epilogue<D>(ep, acc, row, lane);
 }
@@ -304,9 +311,27 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
   const bool has_long = plan && plan->n_long > 0;
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
-  spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-      rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep);
-  count_launch();
+  if (kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
+    const int64_t nA = plan->n_split_rows < n_rows ? plan->n_split_rows : n_rows;
+    Epilogue epA{};
+    epA.Y = plan->hot_partial;
+    const int64_t gridA = (nA + kRowsPerCta - 1) / kRowsPerCta;
+    if (gridA > 0) {
+      spmm_rows_kernel<D, U, kHot><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
+          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1);
+      count_launch();
+    }
+    Epilogue epB = ep;
+    epB.partial_in = plan->hot_partial;
+    epB.n_partial = nA;
+    spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2);
+    count_launch();
+  } else {
+    spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep, nullptr, 0);
+    count_launch();
+  }
   if (has_long) {
     const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
     const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;

@@ -70,6 +70,8 @@ class DeviceGraph:
         self._plan_struct = None
         self._plan_D = 0
         self._plan_tensors = None
+        self.rowmid = None            # first cold edge of every row (SPEX_PLAN_TWO_PASS)
+        self.n_split_rows = 0
         self.col_hot = False          # bit 31 of col flags hot table rows (SPEX_PLAN_COL_HOTBIT)
         if col_hot:                   # a row block cut from an already marked graph
             self.col_hot = True
@@ -225,6 +227,57 @@ class DeviceGraph:
         self._plan_D = 0
         return int(hot.sum())
 
+    def split_hot_cold(self, n_split_rows: Optional[int] = None, chunk_edges: int = 1 << 27) -> int:
+        """Two-pass rows (SPEX_PLAN_TWO_PASS): inside every short row of [0, n_split_rows) move the
+        edges whose column is flagged hot to the front (stable, in place) and remember the first
+        cold edge in `rowmid`.  The SpMM then reduces the hot edges of all those rows first - a pass
+        whose table working set is the hot set only, so it stays in L2 - and the cold edges in a
+        second, purely streaming pass.  Long rows keep their column order (their segment lists
+        depend on it).  Only the summation order inside a row changes.  Returns the hot edges moved.
+        """
+        if not self.col_hot:
+            return 0
+        if self.tpos is not None:
+            raise ValueError("split_hot_cold would invalidate the transpose map (edge dropout graphs)")
+        n_split = self.n_rows if n_split_rows is None else min(int(n_split_rows), self.n_rows)
+        dev = self.device
+        rowptr = self.rowptr
+        rowmid = rowptr[:-1].clone()
+        total_hot = 0
+        rp_host = rowptr[: n_split + 1].cpu()
+        a = 0
+        while a < n_split:
+            # rows [a, b) with at most chunk_edges edges (at least one row)
+            limit = int(rp_host[a]) + chunk_edges
+            b = int(torch.searchsorted(rp_host, torch.tensor(limit), right=True)) - 1
+            b = max(min(b, n_split), a + 1)
+            ea, eb = int(rp_host[a]), int(rp_host[b])
+            if eb > ea:
+                c, v = self.col[ea:eb], self.val[ea:eb]
+                lrp = rowptr[a: b + 1] - ea
+                d = lrp[1:] - lrp[:-1]
+                rid = torch.repeat_interleave(torch.arange(b - a, device=dev), d)
+                h = (c < 0) & (d <= self.seg_len)[rid]
+                cs0 = torch.zeros(eb - ea + 1, dtype=torch.int64, device=dev)
+                cs0[1:] = torch.cumsum(h, 0, dtype=torch.int64)
+                hot_before = cs0[:-1] - cs0[lrp[:-1]][rid]            # hot edges of the row before e
+                hot_cnt = cs0[lrp[1:]] - cs0[lrp[:-1]]
+                pos = torch.arange(eb - ea, device=dev) - lrp[:-1][rid]
+                newpos = lrp[:-1][rid] + torch.where(h, hot_before, hot_cnt[rid] + (pos - hot_before))
+                cn, vn = torch.empty_like(c), torch.empty_like(v)
+                cn[newpos] = c
+                vn[newpos] = v
+                c.copy_(cn)
+                v.copy_(vn)
+                rowmid[a:b] += hot_cnt
+                total_hot += int(hot_cnt.sum())
+                del rid, h, cs0, hot_before, hot_cnt, pos, newpos, cn, vn
+            a = b
+        self.rowmid = rowmid
+        self.n_split_rows = n_split
+        self._plan_D = 0
+        return total_hot
+
     def clean_col(self) -> torch.Tensor:
         """Column indices without the hot flag."""
         return (self.col & 0x7FFFFFFF) if self.col_hot else self.col
@@ -234,19 +287,25 @@ class DeviceGraph:
         if self.n_long == 0 and not self.col_hot:
             return None
         flags = 1 if self.col_hot else 0
-        if self.n_long == 0:
-            if self._plan_D != D:
-                self._plan_struct = LongPlan(self.seg_len, 0, 0, flags, None, None, None, None, None, None)
-                self._plan_D = D
-            return C.byref(self._plan_struct)
+        two = self.col_hot and self.rowmid is not None
+        if two:
+            flags |= 2
         if self._plan_D != D:
-            partial = torch.empty(self.n_seg * D, dtype=torch.float32, device=self.device)
-            st = LongPlan(self.seg_len, self.n_long, self.n_seg, flags, self.long_rows.data_ptr(),
-                          self.long_segptr.data_ptr(), partial.data_ptr(),
-                          self.seg_start.data_ptr() if self.seg_start is not None else None,
-                          self.seg_count.data_ptr() if self.seg_count is not None else None,
-                          self.row_seg.data_ptr() if self.row_seg is not None else None)
-            self._plan_tensors = partial
+            hot_partial = (torch.empty(self.n_split_rows * D, dtype=torch.float32, device=self.device)
+                           if two else None)
+            tail = (self.rowmid.data_ptr() if two else None, hot_partial.data_ptr() if two else None,
+                    self.n_split_rows if two else 0)
+            if self.n_long == 0:
+                st = LongPlan(self.seg_len, 0, 0, flags, None, None, None, None, None, None, *tail)
+                self._plan_tensors = (None, hot_partial)
+            else:
+                partial = torch.empty(self.n_seg * D, dtype=torch.float32, device=self.device)
+                st = LongPlan(self.seg_len, self.n_long, self.n_seg, flags, self.long_rows.data_ptr(),
+                              self.long_segptr.data_ptr(), partial.data_ptr(),
+                              self.seg_start.data_ptr() if self.seg_start is not None else None,
+                              self.seg_count.data_ptr() if self.seg_count is not None else None,
+                              self.row_seg.data_ptr() if self.row_seg is not None else None, *tail)
+                self._plan_tensors = (partial, hot_partial)
             self._plan_struct = st
             self._plan_D = D
         return C.byref(self._plan_struct)

@@ -104,6 +104,36 @@ def test_hot_column_hints_do_not_change_results(cuda_device, seg_len):
     assert int(A.indices()[1].max()) < nu + 1 + m
 
 
+@pytest.mark.parametrize("seg_len", [32, 1024])
+def test_two_pass_hot_cold_rows(cuda_device, seg_len):
+    """SPEX_PLAN_TWO_PASS: hot edges of every short user row are reduced in a first pass, cold
+    edges in a second one that adds the partial row.  Same matrix, only the summation order inside
+    a row changes: parity with torch.sparse.mm at the fp32 bar, reproducible, long rows untouched."""
+    from spex_b200 import ops
+
+    nu, m, D = 900, 500, 64
+    u, i = random_graph(nu, m, 12000, 17, hub_items=4, hub_degree=700)
+    g0 = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    g1 = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    g1.tpos = None
+    assert g1.mark_hot_columns(D, budget_bytes=32 * 1024) > 0
+    moved = g1.split_hot_cold(nu + 1, chunk_edges=3000)
+    assert moved > 0 and g1.rowmid is not None
+    deg = g1.rowptr[1:] - g1.rowptr[:-1]
+    assert bool((g1.rowmid >= g1.rowptr[:-1]).all()) and bool((g1.rowmid <= g1.rowptr[1:]).all())
+    assert bool((g1.rowmid[nu + 1:] == g1.rowptr[nu + 1: -1]).all())          # item rows: no hot pass
+    assert bool((g1.rowmid[: nu + 1][deg[: nu + 1] > seg_len] == g1.rowptr[: nu + 1][deg[: nu + 1] > seg_len]).all())
+    torch.manual_seed(0)
+    X = torch.randn(nu + 1 + m, D, device=cuda_device)
+    A = g0.to_sparse_coo()
+    want = torch.sparse.mm(A, X)
+    got = ops.spmm(g1, X)
+    assert rel_err(got, want) < TOL
+    assert torch.equal(got, ops.spmm(g1, X))
+    E = X * 0.1
+    assert rel_err(ops.propagate_mean(E, g1, 3), ops.propagate_mean(E, g0, 3)) < TOL
+
+
 @pytest.mark.parametrize("K", [0, 1, 2, 3, 4])
 def test_propagate_mean_and_determinism(cuda_device, K):
     from spex_b200 import ops
