@@ -330,6 +330,8 @@ def run_ours(args):
         prop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
         if args.e0_exchange is not None and args.exchange != "nccl":
             prop.e0_exchange = args.e0_exchange   # default: nccl in push mode, mcast in mcast mode
+        elif args.exchange == "push" and world == 2:
+            prop.e0_exchange = "push"             # 2 GPUs: one peer, P2P stores beat the NCCL path (95 vs 115 ms/step)
         local_nnz, local_rows = hi - lo, r1 - r0
 
         def step():
