@@ -227,6 +227,10 @@ def run_ours(args):
     hot_edges = 0
     if world == 1 and n_hot > 0 and os.environ.get("SPEX_TWO_PASS"):
         hot_edges = g.split_hot_cold(nur)
+    # optional (SPEX_INTERLEAVE=1): schedule user rows (L2-served gathers of popular items) and item rows
+    # (DRAM-served gathers of random users) interleaved.  Measured slower (184.9 vs 176.7 ms): off.
+    if world == 1 and os.environ.get("SPEX_INTERLEAVE"):
+        g.set_row_classes(nur)
     nnz = g.nnz
     table = synthetic.xavier_table(nur, m, D, 2020, dev)
     torch.cuda.synchronize()
@@ -542,7 +546,7 @@ def run_ours(args):
                        "parallelism": f"row-partition x{world}" + (f" exchange={args.exchange}" + (f" e0={prop.e0_exchange}" if args.exchange != "nccl" else "")
                                                                        if world > 1 else ""),
                        "graph_build_s": round(t_gen, 2), "hot_rows_kept_in_l2": n_hot,
-                       "two_pass_hot_edges": hot_edges,
+                       "two_pass_hot_edges": hot_edges, "interleaved_row_classes": int(world == 1 and g.interleave_split > 0) if world == 1 else 0,
                        "balance_ms_per_rank": balance_log if world > 1 else None,
                        "phase_ms_max_over_ranks": phase_log},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "parity": parity,

@@ -64,6 +64,11 @@ int64_t spex_launch_count(void);
  * hot_partial; pass B reduces the cold edges (pure streaming) and adds the partial row.  Needs
  * SPEX_PLAN_COL_HOTBIT. */
 #define SPEX_PLAN_TWO_PASS 2
+/* rows [0, interleave_split) and [interleave_split, n_rows) are two classes with different
+ * bottlenecks (user rows gather popular item rows out of L2, item rows gather random user rows out
+ * of DRAM): the short-row kernel visits them interleaved in proportion, so that L2-bound and
+ * DRAM-bound work overlap instead of running one after the other. */
+#define SPEX_PLAN_INTERLEAVE 4
 
 typedef struct spex_long_plan {
   int32_t seg_len;            /* rows with degree > seg_len take the long-row path (>= 32)    */
@@ -79,6 +84,7 @@ typedef struct spex_long_plan {
   const int64_t* rowmid;      /* int64 [n_rows]  SPEX_PLAN_TWO_PASS: first cold edge of every row */
   float* hot_partial;         /* fp32  [n_split_rows, D] workspace of pass A                   */
   int64_t n_split_rows;       /* rows [0, n_split_rows) take part in pass A                    */
+  int64_t interleave_split;   /* SPEX_PLAN_INTERLEAVE: first row of the second class           */
 } spex_long_plan;
 
 /*

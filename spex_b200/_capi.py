@@ -35,6 +35,7 @@ class LongPlan(C.Structure):
         ("rowmid", _p),
         ("hot_partial", _p),
         ("n_split_rows", _i64),
+        ("interleave_split", _i64),
     ]
 
 

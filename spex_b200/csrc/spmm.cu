@@ -162,10 +162,18 @@ template <int D, int U, bool kHot>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
-                 int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass) {
+                 int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass,
+                 int64_t split) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
+  if (split > 0) {
+    // SPEX_PLAN_INTERLEAVE: slot b -> rows of class A = [0, split) and class B = [split, n_rows)
+    // taken in proportion (B gets slot b iff floor((b+1) nb / n) > floor(b nb / n)); a bijection
+    const int64_t nb = n_rows - split;
+    const int64_t kb = (row * nb) / n_rows, kb1 = ((row + 1) * nb) / n_rows;
+    row = (kb1 > kb) ? split + kb : row - kb;
+  }
   int64_t start = rowptr[row], end = rowptr[row + 1];
   if (skip_longer_than > 0 && end - start > skip_longer_than) return;  // long-row path
   // two-pass rows: pass 1 = hot edges [start, rowmid), pass 2 = cold edges [rowmid, end)
@@ -311,6 +319,10 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
   const bool has_long = plan && plan->n_long > 0;
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
+  const int64_t split = (plan && (plan->flags & SPEX_PLAN_INTERLEAVE) && plan->interleave_split > 0 &&
+                         plan->interleave_split < n_rows)
+                            ? plan->interleave_split
+                            : 0;
   if (kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
     const int64_t nA = plan->n_split_rows < n_rows ? plan->n_split_rows : n_rows;
     Epilogue epA{};
@@ -318,18 +330,18 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
     const int64_t gridA = (nA + kRowsPerCta - 1) / kRowsPerCta;
     if (gridA > 0) {
       spmm_rows_kernel<D, U, kHot><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
-          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1);
+          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0);
       count_launch();
     }
     Epilogue epB = ep;
     epB.partial_in = plan->hot_partial;
     epB.n_partial = nA;
     spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2);
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split);
     count_launch();
   } else {
     spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep, nullptr, 0);
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep, nullptr, 0, split);
     count_launch();
   }
   if (has_long) {

@@ -70,6 +70,7 @@ class DeviceGraph:
         self._plan_struct = None
         self._plan_D = 0
         self._plan_tensors = None
+        self.interleave_split = 0     # first row of the second row class (SPEX_PLAN_INTERLEAVE)
         self.rowmid = None            # first cold edge of every row (SPEX_PLAN_TWO_PASS)
         self.n_split_rows = 0
         self.col_hot = False          # bit 31 of col flags hot table rows (SPEX_PLAN_COL_HOTBIT)
@@ -278,23 +279,33 @@ class DeviceGraph:
         self._plan_D = 0
         return total_hot
 
+    def set_row_classes(self, split: int):
+        """SPEX_PLAN_INTERLEAVE: rows [0, split) (users) and [split, n_rows) (items) are visited
+        interleaved in proportion by the short-row kernel.  0 turns it off.  Results are unchanged
+        (only the order in which rows are scheduled moves)."""
+        self.interleave_split = int(split)
+        self._plan_D = 0
+
     def clean_col(self) -> torch.Tensor:
         """Column indices without the hot flag."""
         return (self.col & 0x7FFFFFFF) if self.col_hot else self.col
 
     def plan(self, D: int):
         """ctypes pointer to a spex_long_plan for embedding width D (NULL if nothing to say)."""
-        if self.n_long == 0 and not self.col_hot:
+        inter = 0 < self.interleave_split < self.n_rows
+        if self.n_long == 0 and not self.col_hot and not inter:
             return None
         flags = 1 if self.col_hot else 0
         two = self.col_hot and self.rowmid is not None
         if two:
             flags |= 2
+        if inter:
+            flags |= 4
         if self._plan_D != D:
             hot_partial = (torch.empty(self.n_split_rows * D, dtype=torch.float32, device=self.device)
                            if two else None)
             tail = (self.rowmid.data_ptr() if two else None, hot_partial.data_ptr() if two else None,
-                    self.n_split_rows if two else 0)
+                    self.n_split_rows if two else 0, self.interleave_split if inter else 0)
             if self.n_long == 0:
                 st = LongPlan(self.seg_len, 0, 0, flags, None, None, None, None, None, None, *tail)
                 self._plan_tensors = (None, hot_partial)

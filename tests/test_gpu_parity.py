@@ -102,6 +102,13 @@ def test_hot_column_hints_do_not_change_results(cuda_device, seg_len):
     assert torch.equal(ops.propagate_mean(E, g1, 3), ops.propagate_mean(E, g0, 3))
     A = g1.to_sparse_coo()
     assert int(A.indices()[1].max()) < nu + 1 + m
+    # SPEX_PLAN_INTERLEAVE only changes the order in which rows are scheduled
+    g1.set_row_classes(nu + 1)
+    assert torch.equal(ops.spmm(g1, X), ops.spmm(g0, X))
+    assert torch.equal(ops.propagate_mean(E, g1, 3), ops.propagate_mean(E, g0, 3))
+    g2 = _dev_graph(u, i, nu + 1, m, cuda_device, seg_len)
+    g2.set_row_classes(nu + 1)                      # without hot flags: plan carries only the split
+    assert torch.equal(ops.spmm(g2, X), ops.spmm(g0, X))
 
 
 @pytest.mark.parametrize("seg_len", [32, 1024])
