@@ -258,3 +258,30 @@ def test_ngcf_adjacency_builder_edge_cases():
     assert np.array_equal(h.tpos, g.tpos)
     with pytest.raises(ValueError):
         build_ngcf_norm_adj(np.array([5]), np.array([0]), nu, ni)
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference (the reference's CPU path, oracle port) prints ONE JSON line with
+    the keys the driver reads; the product arm refuses to run without a GPU instead of falling back."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-sample-scale", "0.001"], cwd=root, env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "lightgcn_propagation_gedges_per_s"
+    assert j["unit"] == "GEdges/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["sample"]
+    assert j["cpu_baseline"]["value"] == j["value"] == j["e2e"]["value"]
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    assert j["gpu_launches"] == 0 and "workload" in j["config"]
+    ours = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=root, env=env,
+                          capture_output=True, text=True, timeout=600)
+    assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
