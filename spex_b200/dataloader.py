@@ -356,6 +356,42 @@ def _sample_stream_exact(slots_u, neg, num_item, contains, chunk: int = 65536, w
             p += f + 1  # the colliding draw is consumed; slot s retries with the next draw
 
 
+def uniform_sample_bpr(train_users, train_items, n_users: int, m_items: int, n_samples: Optional[int] = None,
+                       seed: int = 2020) -> np.ndarray:
+    """(user, positive, negative) triples for ``LightGCN.bpr_loss`` - int64 [n, 3].
+
+    The reference has no BPR path (SURVEY "five facts" #2); the semantics are those of the upstream
+    LightGCN-PyTorch sampler the reference was derived from (README.md:29): draw ``n_samples``
+    (default: the number of training pairs) users uniformly WITH replacement, skip users without
+    interactions, take one of the user's training items uniformly as the positive and rejection-
+    sample a negative that is not a training item of the user.  Vectorised: positives come from the
+    interaction CSR, negatives are drawn for all triples at once and only collisions are redrawn.
+    North-star semantics, not reference-pinned; deterministic in ``seed``.
+    """
+    tu = np.asarray(train_users, dtype=np.int64).ravel()
+    ti = np.asarray(train_items, dtype=np.int64).ravel()
+    rng = np.random.default_rng(seed)
+    n = tu.size if n_samples is None else int(n_samples)
+    key = np.unique(tu * m_items + ti)                   # sorted (user, item) pairs, duplicates dropped
+    ku, ki = key // m_items, key % m_items
+    deg = np.bincount(ku, minlength=n_users)
+    rp = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(deg, out=rp[1:])
+    users = rng.integers(0, n_users, n)
+    users = users[deg[users] > 0]
+    pos = ki[rp[users] + (rng.random(users.size) * deg[users]).astype(np.int64)]
+    neg = np.empty(users.size, dtype=np.int64)
+    todo = np.arange(users.size)
+    while todo.size:
+        draw = rng.integers(0, m_items, todo.size)
+        neg[todo] = draw
+        k = users[todo] * m_items + draw
+        p = np.searchsorted(key, k)
+        p[p == key.size] = 0
+        todo = todo[key[p] == k] if key.size else todo[:0]
+    return np.stack([users, pos, neg], axis=1)
+
+
 class SyntheticDataset(_GraphMixin, BasicDataset):
     """Seeded synthetic bipartite interactions with the dataset surface the model and the
     evaluation harness read (n_users, m_items, trainUser/trainItem, testRatings, testNegatives).

@@ -285,3 +285,28 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
     ours = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=root, env=env,
                           capture_output=True, text=True, timeout=600)
     assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
+
+
+def test_bpr_triple_sampler():
+    """uniform_sample_bpr (upstream-LightGCN semantics for the north-star bpr_loss): positives are
+    training items of the user, negatives are not, users without interactions never appear, the
+    draw is deterministic in the seed and roughly uniform over active users."""
+    from spex_b200.dataloader import uniform_sample_bpr
+
+    nu, m = 200, 60
+    u, i = random_graph(nu, m, 3000, 5)
+    keep = u != 7                                    # user 7 has no interactions
+    u, i = u[keep], i[keep]
+    S = uniform_sample_bpr(u, i, nu, m, n_samples=20000, seed=1)
+    assert S.dtype == np.int64 and S.shape[1] == 3 and 19000 < S.shape[0] <= 20000
+    train = set(zip(u.tolist(), i.tolist()))
+    assert all((a, b) in train for a, b, _ in S[:2000].tolist())
+    assert not any((a, c) in train for a, _, c in S.tolist())
+    assert 7 not in set(S[:, 0].tolist())
+    assert 0 <= S[:, 2].min() and S[:, 2].max() < m
+    assert np.array_equal(S, uniform_sample_bpr(u, i, nu, m, n_samples=20000, seed=1))
+    assert not np.array_equal(S, uniform_sample_bpr(u, i, nu, m, n_samples=20000, seed=2))
+    counts = np.bincount(S[:, 0], minlength=nu)
+    active = np.unique(u)
+    assert counts[active].min() > 40 and counts[active].max() < 170      # ~100 each
+    assert uniform_sample_bpr(u, i, nu, m).shape[0] <= u.size
