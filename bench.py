@@ -403,6 +403,10 @@ def run_ours(args):
                                           "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                # frac > 1 is possible: the algorithmic bytes assume no cache reuse, L2 serves part of
+                # the gathers.  The DRAM-side view of the same launch: measured traffic / time / peak.
+                "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,
+                "dram_frac": (traffic / t_launch / 1e9 / hbm_peak) if traffic else None,
                 "note": "per-launch time = step time / K (exchange included at N>1); traffic from ncu, "
                         "per layer"}
 
