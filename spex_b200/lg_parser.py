@@ -1,30 +1,46 @@
-"""Command-line flags of the LightGCN_SPEX entry points: same names, types and defaults as
-/root/reference/LightGCN_SPEX/code/lg_parser.py:3-24, plus --data_path being honoured by Loader
-(the reference parses it but hard-codes "../data/", dataloader.py:74)."""
+"""Command-line surface of the LightGCN_SPEX entry points.
+
+The flag NAMES, types and defaults are the contract (the model and the loaders read
+``args.recdim / layer / keepprob / A_split / dropout / a_fold / dataset ...``); they are those of
+/root/reference/LightGCN_SPEX/code/lg_parser.py:3-24.  Differences: ``--data_path`` is honoured by
+``Loader`` (the reference parses it but hard-codes "../data/", dataloader.py:74) and ``parse_args_r``
+accepts an explicit argv for tests.
+"""
 import argparse
 
+# (flag, type or None for a switch, default, what it controls here)
+_FLAGS = (
+    ("cuda_id", str, "0", "CUDA_VISIBLE_DEVICES for the run"),
+    ("data_path", str, "../data/", "directory that holds <dataset>/rec/*.rating|negative"),
+    ("dataset", str, "twitter", "epinion2 | weibo | twitter (directory name under data_path)"),
+    ("nb_heads", int, 3, "attention heads of the path-prediction task (main_11)"),
+    ("recdim", int, 64, "embedding width D (the sm_100a fast paths are built for 32/64/128)"),
+    ("layer", int, 3, "propagation depth K of computer()"),
+    ("lr", float, 0.001, "Adam step size"),
+    ("dropout", int, 0, "1 = edge dropout on the normalised adjacency while training"),
+    ("keepprob", float, 0.6, "probability that an edge survives the dropout"),
+    ("a_fold", int, 100, "row folds of the adjacency when A_split is on"),
+    ("epochs", int, 50, "training epochs"),
+    ("seed", int, 2020, "seed of every generator"),
+    ("A_split", int, 0, "1 = getSparseGraph() returns a_fold row blocks"),
+    ("batch_size", int, 256, "(kept for compatibility; the rec loader uses 256)"),
+    ("batchSize", int, 256, "paths per batch of the path-prediction task"),
+    ("hiddenSize", int, 64, "hidden width of the path-prediction task"),
+    ("nonhybrid", None, False, "path task: global preference only"),
+    ("act", int, 1, "activation selector of the path task"),
+)
 
-def build_parser():
-    p = argparse.ArgumentParser(description="Go lightGCN")
-    p.add_argument("--cuda_id", default="0", help="which device to use")
-    p.add_argument("--data_path", nargs="?", default="../data/", help="Input data path.")
-    p.add_argument("--dataset", type=str, default="twitter", help="available datasets: [epinion2,weibo,twitter]")
-    p.add_argument("--nb_heads", type=int, default=3, help="Number of head attentions.")
-    p.add_argument("--recdim", type=int, default=64, help="the embedding size of lightGCN")
-    p.add_argument("--layer", type=int, default=3, help="the layer num of lightGCN")
-    p.add_argument("--lr", type=float, default=0.001, help="the learning rate")
-    p.add_argument("--dropout", type=int, default=0, help="using the dropout or not")
-    p.add_argument("--keepprob", type=float, default=0.6, help="edge keep probability of the dropout graph")
-    p.add_argument("--a_fold", type=int, default=100, help="the fold num used to split large adj matrix")
-    p.add_argument("--epochs", type=int, default=50)
-    p.add_argument("--seed", type=int, default=2020, help="random seed")
-    p.add_argument("--A_split", type=int, default=0, help="")
-    p.add_argument("--batch_size", type=int, default=256, help="")
-    p.add_argument("--batchSize", type=int, default=256, help="input batch size")
-    p.add_argument("--hiddenSize", type=int, default=64, help="hidden state size")
-    p.add_argument("--nonhybrid", action="store_true", help="only use the global preference to predict")
-    p.add_argument("--act", type=int, default=1, help="activation function")
-    return p
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="LightGCN_SPEX on spex_b200")
+    for name, kind, default, doc in _FLAGS:
+        if kind is None:
+            parser.add_argument("--" + name, action="store_true", help=doc)
+        elif name == "data_path":
+            parser.add_argument("--" + name, nargs="?", default=default, help=doc)
+        else:
+            parser.add_argument("--" + name, type=kind, default=default, help=doc)
+    return parser
 
 
 def parse_args_r(argv=None):

@@ -310,3 +310,17 @@ def test_bpr_triple_sampler():
     active = np.unique(u)
     assert counts[active].min() > 40 and counts[active].max() < 170      # ~100 each
     assert uniform_sample_bpr(u, i, nu, m).shape[0] <= u.size
+
+
+def test_parser_keeps_the_reference_namespace():
+    """Flag names, types and defaults of /root/reference/LightGCN_SPEX/code/lg_parser.py:3-24."""
+    from spex_b200.lg_parser import parse_args_r
+
+    want = {"cuda_id": "0", "data_path": "../data/", "dataset": "twitter", "nb_heads": 3, "recdim": 64,
+            "layer": 3, "lr": 0.001, "dropout": 0, "keepprob": 0.6, "a_fold": 100, "epochs": 50,
+            "seed": 2020, "A_split": 0, "batch_size": 256, "batchSize": 256, "hiddenSize": 64,
+            "nonhybrid": False, "act": 1}
+    got = vars(parse_args_r([]))
+    assert got == want and all(type(got[k]) is type(v) for k, v in want.items())
+    a = parse_args_r(["--dataset", "epinion2", "--layer", "2", "--nonhybrid", "--keepprob", "0.3", "--A_split", "1"])
+    assert (a.dataset, a.layer, a.nonhybrid, a.keepprob, a.A_split) == ("epinion2", 2, True, 0.3, 1)
