@@ -202,7 +202,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+        # NCCL_DEBUG is left as the caller set it: the driver reads NCCL's own lines to count ranks
         dist.init_process_group("nccl", device_id=dev)
 
     from spex_b200 import ops, synthetic

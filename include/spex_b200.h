@@ -252,6 +252,34 @@ int spex_score_topk_bf16(const void* Ub, const void* Ib, int64_t B, int64_t B_pa
                          int32_t k, int32_t* out_idx, float* out_val, void* stream);
 
 /*
+ * fp32 [rows, D] -> fp16( x * 2^s ) in the same UMMA K-major no-swizzle layout as spex_pack_bf16.
+ * s is chosen on the device so that every scaled row norm is < 2^7 (no fp16 overflow anywhere in
+ * a score, |score| < 2^14):  meta4 (device fp32 [4], 16-byte aligned) receives
+ *   meta4[0] = 2^s, meta4[1] = 2^-s, meta4[2] = max scaled row norm, meta4[3] = max row norm^2.
+ * Feeds spex_score_topk_f16 (operands of NGCF_SPEX/code/utility/batch_test.py:158's matmul).
+ */
+int spex_pack_f16(const float* src, const int64_t* rows, int64_t n, int64_t n_pad, int32_t D,
+                  void* dst_f16, float* meta4, void* stream);
+
+/*
+ * Full-ranking top-k, fp16-accumulator tensor-core filter + exact fp32 re-score (D == 64 or 128).
+ * Uh [B_pad, D] / Ih [m_pad, D] and u_meta / i_meta come from spex_pack_f16.  The tensor core
+ * (tcgen05.mma kind::f16, fp16 accumulators: half the TMEM -> register drain of the bf16/fp32
+ * kernel) only FILTERS against  tau - eps;  every survivor is re-scored in fp32 from the fp16
+ * operands, so the result is the exact top-k of  <fp16(U 2^su), fp16(I 2^si)> 2^-(su+si)
+ * (score descending, ties by ascending item id; values in the original units).  Mask, user_ids,
+ * outputs and k <= 64 as spex_score_topk_bf16.  No workspace.
+ * Replaces torch.matmul(u_g_embeddings, i_g_embeddings^T) + the ranking that follows it
+ * (NGCF_SPEX/code/utility/batch_test.py:158) and serves LightGCN.getUsersRating + top-k
+ * (abstract at LightGCN_SPEX/code/utility1/model.py:14-15).
+ */
+int spex_score_topk_f16(const void* Uh, const void* Ih, int32_t D, int64_t B, int64_t B_pad,
+                        int64_t m_items, int64_t m_pad, const float* u_meta, const float* i_meta,
+                        const int64_t* user_ids, const int64_t* mask_rowptr,
+                        const int32_t* mask_col, int32_t k, int32_t* out_idx, float* out_val,
+                        void* stream);
+
+/*
  * Sampled-candidate scoring for the reference Test() (batch_test.py:28-40, hoisted):
  *   score[u,c] = <U[users[u]], I[cand[u,c]]>,  cand int32 [n_u, n_c]  ->  score fp32 [n_u, n_c]
  */

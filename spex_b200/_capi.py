@@ -62,6 +62,8 @@ SIGNATURES = {
     "spex_rating_f32": (C.c_int, [_p, _p, _i32, _p, _i64, _i64, _i32, _p, _p]),
     "spex_pack_bf16": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p]),
     "spex_score_topk_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p]),
+    "spex_pack_f16": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "spex_score_topk_f16": (C.c_int, [_p, _p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "spex_score_candidates_f32": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),
     "spex_ngcf_epilogue_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f, _p, _p, _i64, _p]),
     "spex_ipc_alloc": (C.c_int, [_i64, C.POINTER(_p), _p]),
@@ -96,9 +98,20 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale: loud on purpose
         fn.restype = res
         fn.argtypes = args
+    # sm_100a only, import fails loudly on any other GPU.  A box with no CUDA device at
+    # all (the CPU build/test container) may still import the binding to check the exported ABI;
+    # every compute entry point fails there on its own.
+    sm, ma, mi = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib.spex_device_check(C.byref(sm), C.byref(ma), C.byref(mi))
+    if rc == SPEX_E_ARCH:
+        raise ImportError(
+            f"spex_b200 is built for sm_100a (B200) only; the current device is sm_{ma.value}{mi.value}. "
+            "There is no fallback path."
+        )
     return lib
 
 
+SPEX_E_ARCH = -4  # include/spex_b200.h
 lib = _load()
 
 

@@ -593,12 +593,11 @@ static int tc_launch(const void* Ub, const void* Ib, int64_t B, int64_t B_pad, i
   if (const char* e = getenv("SPEX_TC_STAGES")) stages = atoi(e);   // bring-up experiment
   const size_t smem = tc_smem_bytes(32 * EPL, stages);
   SPEX_RETURN_IF(smem > 226 * 1024, SPEX_E_TOOBIG);
-  static bool configured = false;
-  if (!configured) {
+  // per device and per function, and the size depends on `stages`: set on every launch (cheap)
+  {
     cudaError_t e = cudaFuncSetAttribute(tc::score_topk_tc_kernel<EPL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   const int64_t grid = B_pad / tc::BM;
   SPEX_RETURN_IF(grid > 0x7fffffffLL, SPEX_E_TOOBIG);

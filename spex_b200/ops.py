@@ -609,6 +609,46 @@ def score_topk_bf16(Ub, B, B_pad, Ib, m_items, m_pad, k, user_ids=None, mask_row
     return out_idx, out_val
 
 
+def pack_f16(src, rows=None, row_multiple: int = 8, out=None):
+    """fp32 [n, D] (optionally gathered by `rows`) -> scaled fp16 UMMA layout + its meta (scale,
+    1/scale, max scaled row norm, max row norm^2): the operands of score_topk_f16."""
+    _need_cuda(src)
+    src = _f32c(src)
+    dev = src.device
+    n = src.shape[0] if rows is None else rows.numel()
+    D = src.shape[1]
+    n_pad = (n + row_multiple - 1) // row_multiple * row_multiple
+    if out is None:
+        out = torch.empty(n_pad * D, dtype=torch.float16, device=dev)
+    elif out.numel() < n_pad * D:
+        raise ValueError("pack_f16: output buffer too small")
+    meta = torch.empty(4, dtype=torch.float32, device=dev)
+    rows_t = None if rows is None else _i64c(rows, dev)
+    call("spex_pack_f16", ptr(src), ptr(rows_t), n, n_pad, D, ptr(out), ptr(meta), stream_ptr())
+    return out, n_pad, meta
+
+
+def score_topk_f16(Uh, u_meta, B, B_pad, Ih, i_meta, m_items, m_pad, D, k, user_ids=None,
+                   mask_rowptr=None, mask_col=None, out_idx=None, out_val=None):
+    """tcgen05 fp16-accumulator filter + exact fp32 re-score, fused mask + per-row top-k
+    (D = 64 or 128; NGCF_SPEX/code/utility/batch_test.py:158 semantics + ranking)."""
+    _need_cuda(Uh, Ih)
+    if not 1 <= k <= TC_MAX_K:
+        raise ValueError(f"score_topk_f16: k must be in [1, {TC_MAX_K}] (use score_topk_f32 beyond)")
+    if D not in (64, 128):
+        raise ValueError("score_topk_f16: D must be 64 or 128 (use score_topk_f32 otherwise)")
+    dev = Uh.device
+    if out_idx is None:
+        out_idx = torch.empty(B, k, dtype=torch.int32, device=dev)
+    if out_val is None:
+        out_val = torch.empty(B, k, dtype=torch.float32, device=dev)
+    uid = None if user_ids is None else _i64c(user_ids, dev)
+    call("spex_score_topk_f16", ptr(Uh), ptr(Ih), int(D), B, B_pad, m_items, m_pad, ptr(u_meta),
+         ptr(i_meta), ptr(uid), ptr(mask_rowptr), ptr(mask_col), int(k), ptr(out_idx), ptr(out_val),
+         stream_ptr())
+    return out_idx, out_val
+
+
 GATE_BWD_BLOCKS = 1184  # SPEX_GATE_BWD_BLOCKS in include/spex_b200.h
 
 
@@ -638,7 +678,18 @@ class _ExpertGate(torch.autograd.Function):
 
 
 def expert_gate(E0, Eout, W):
-    """softmax([E0|Eout].W) convex mix per row (model_expert_s.py:154-161), differentiable."""
+    """softmax([E0|Eout].W) convex mix per row (model_expert_s.py:154-161), differentiable.
+
+    The reference multiplies cat([E0, Eout], 1) [n, 2D] by att_exp [2*hiddenSize, 2]
+    (model_expert_s.py:158-161) and raises a shape error when hiddenSize != recdim; so do we.
+    """
+    D = E0.shape[1]
+    if E0.shape != Eout.shape:
+        raise ValueError(f"expert_gate: E0 {tuple(E0.shape)} and Eout {tuple(Eout.shape)} differ")
+    if tuple(W.shape) != (2 * D, 2):
+        raise ValueError(f"expert_gate: gate weights must be [{2 * D}, 2] (2*recdim x 2), got {tuple(W.shape)}")
+    if D > 128 or D % 4:
+        raise ValueError("expert_gate: recdim must be a multiple of 4 and <= 128")
     return _ExpertGate.apply(E0, Eout, W)
 
 
