@@ -310,6 +310,11 @@ int spex_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64_host);
  * [out_row_offset, out_row_offset + n_rows) of each of the n_peers (<= 8) tables (own included). */
 int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
                        float* const* peer_Y_host, int32_t n_peers, void* stream);
+/* the same with an explicit grid: n_ctas == 0 is the full-speed grid; a small n_ctas (e.g. the SM
+ * count) makes it a BACKGROUND exchange that can run next to a layer kernel on a high-priority
+ * stream (spex_b200/dist.py: the next call's E^(0) is published while the last layer runs). */
+int spex_push_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                          float* const* peer_Y_host, int32_t n_peers, int32_t n_ctas, void* stream);
 int spex_ipc_open(const void* handle64_host, void** dev_ptr);
 int spex_ipc_close(void* dev_ptr);
 int spex_ipc_free(void* dev_ptr);
@@ -322,6 +327,8 @@ int spex_spmm_csr_f32_mcast(const int64_t* rowptr, const int32_t* col, const flo
                             float z_scale, const spex_long_plan* plan, void* stream);
 int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
                         float* mcast_Y, void* stream);
+int spex_mcast_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                           float* mcast_Y, int32_t n_ctas, void* stream);
 /* cudaMemcpyAsync(DeviceToDevice) on `stream`: a copy-engine transfer into an IPC-mapped peer
  * table (dst may be peer memory), used for the E^(0) all-gather so that no SM is involved. */
 int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream);

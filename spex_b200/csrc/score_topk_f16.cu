@@ -13,20 +13,29 @@
 //     every row norm is below 2^7: no overflow, |score| < 2^14), same UMMA no-swizzle K-major
 //     canonical layout as before (8-row x 16-byte core matrices, one bulk copy per tile);
 //   * the tensor core accumulates in fp16 (tcgen05.mma.kind::f16, c_format = F16).  That result
-//     `a` is only a FILTER: |a - s| <= eps_u = 2^-8 |u| Vmax + 2^-10 for the exact score s of the
-//     same fp16 operands (four K=16 steps, each rounding a partial sum that is bounded by |u||v|;
-//     2^-8 covers round-toward-zero at every step, the measured error is ~2^-14 |u||v|);
-//   * an epilogue thread owns one user row: ONE tcgen05.ld.x64.pack::16b brings the 128 scores of
-//     its row into 64 registers, the accumulator buffer is handed back to the MMA warp at once,
-//     63 HMNMX2 + one compare + one vote reject the tile against  thr = rd_half(tau - eps_u),
-//     tau = the row's exact k-th best so far;
-//   * survivors (a >= thr; ~k ln(m/k) (1 + few %) per row over the whole sweep) are re-scored
-//     EXACTLY by their own lane: fp32 FMA chain over the fp16 operands (user row from the resident
-//     A tile in shared memory, item row from the packed table in L2), after the merge-cursor test
-//     against the user's training items; only exact scores enter the candidate buffer, whose
-//     warp-cooperative compaction (rank by counting, ties by ascending item id) is unchanged.
-//     The output is therefore the exact top-k of the fp32 scores of the fp16 operands: the filter
-//     can only let extra items through, never drop one (tests/test_gpu_f16_scorer.py);
+//     `a` is only a FILTER: |a - s| <= eps_u = 2^-9 |u| Vmax + 2^-10 for the exact score s of the
+//     same fp16 operands (four K=16 steps, each rounding a partial sum bounded by sum|u_d v_d| <=
+//     |u||v| to fp16: 4 * 2^-12 with round-to-nearest, 4 * 2^-11 = 2^-9 even with truncation;
+//     measured ~2^-14 |u||v|, profiles/microbench/f16acc_b200.txt);
+//   * an epilogue thread owns one user row.  The 128 scores of its row arrive as two half tiles
+//     (tcgen05.ld.32x32b.x32.pack::16b: 64 columns in 32 registers) rotating through THREE
+//     register sets, so that the TMEM read of the next tile is in flight while the current one is
+//     reduced; the accumulator buffer is handed back to the MMA warp as soon as both halves are
+//     in registers.  31 HMNMX2 + one compare + one vote reject a half tile against the row's
+//     threshold thr;
+//   * survivors (a >= thr; ~k ln(m/k) (1 + some %) per row over the whole sweep) pass the merge-
+//     cursor test against the user's training items and are appended, with their filter score and
+//     a flag, to the row's candidate buffer in shared memory (two stores: the survivor path does no
+//     global load).  A full buffer is compacted by the warp WITHOUT leaving the SM: with A = the
+//     k-th largest value held, everything below A - 2 eps is provably outside the top-k and thr
+//     becomes A - 2 eps.  Only when near-ties crowd the buffer, and once at the end, the flagged
+//     entries are re-scored EXACTLY, 32 in parallel (fp32 FMA chain over the fp16 operands: user row
+//     from the resident A tile, item row from the packed table in L2), ties by ascending item id.
+//     History (profiles/r02_tf_scorer.md): re-scoring every survivor at once cost 46 % of the
+//     kernel (770 TF), re-scoring at every compaction 32 % (941 TF), compaction on filter values
+//     966 TF; the filter alone runs at 1430 TF, the MMA side alone at 1560.
+//     The filter can only let extra items through, never drop one, so the output is the exact
+//     top-k of the fp32 scores of the fp16 operands (tests/test_gpu_f16_scorer.py);
 //   * D = 64 (4 MMAs per tile, two CTAs per SM) and D = 128 (8 MMAs, NGCF's concatenated layer
 //     outputs, NGCF_SPEX/code/main_rec.py:85; one CTA per SM).
 //   * warp roles as in round 1: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer
@@ -46,9 +55,8 @@ constexpr int kMaxStages = 4;
 constexpr int kTmemCols = 256;     // 2 accumulator buffers x 128 columns (fp16 accumulators still
                                    // occupy one 32-bit cell each); two CTAs share an SM at D = 64
 constexpr int KMAX_TC = 64;
-constexpr int kGroup = 8;          // appends are capacity-checked every 8 columns
 constexpr uint32_t kSpinLimit = 1u << 26;   // bounded waits: trap instead of hanging the GPU
-constexpr float kEpsRel = 1.0f / 256.0f;    // 2^-8, see the header comment
+constexpr float kEpsRel = 1.0f / 512.0f;    // 2^-9, see the header comment
 constexpr float kEpsAbs = 1.0f / 1024.0f;   // subnormal flush of tiny operands (bound 2^-11)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -142,20 +150,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
       "+r"(r[o + 21]), "+r"(r[o + 22]), "+r"(r[o + 23]), "+r"(r[o + 24]), "+r"(r[o + 25]),          \
       "+r"(r[o + 26]), "+r"(r[o + 27]), "+r"(r[o + 28]), "+r"(r[o + 29]), "+r"(r[o + 30]),          \
       "+r"(r[o + 31])
-__device__ __forceinline__ void tmem_ld128h_issue(uint32_t taddr, uint32_t (&r)[64]) {
+// tcgen05.ld of 32 lanes x 64 columns of fp16 accumulators into 32 registers, without waiting
+__device__ __forceinline__ void tmem_ld64h_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 "
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-      "%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,"
-      "%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-      : SPEX_O32(r, 0), SPEX_O32(r, 32)
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : SPEX_O32(r, 0)
       : "r"(taddr)
       : "memory");
 }
-// wait for the outstanding tcgen05.ld of this thread; the "+r" operands tie the loaded registers
-// to the wait so that no consumer can be scheduled above it
-__device__ __forceinline__ void tmem_wait64(uint32_t (&r)[64]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : SPEX_IO32(r, 0), SPEX_IO32(r, 32) : : "memory");
+// wait for the outstanding tcgen05.ld of this thread; the "+r" operands tie the loaded registers of
+// both half tiles to the wait so that no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_wait2(uint32_t (&x)[32], uint32_t (&y)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SPEX_IO32(x, 0), SPEX_IO32(y, 0) : : "memory");
 }
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -209,29 +217,75 @@ __device__ __forceinline__ float exact_score(const uint8_t* a_row, const uint8_t
   return s;
 }
 
-// One group of 8 columns (4 packed registers) has at least one lane with a filter hit.  Called by
+constexpr int kApprox = (int)0x80000000;   // flag in a candidate's id: its score is still the fp16 filter value
+
+// rank of every entry of a row's buffer under (score desc, id asc): entries travel by warp shuffle,
+// every lane counts the entries that beat its own (a strict total order, so ranks are a permutation)
+template <int EPL>
+__device__ __forceinline__ void rank_entries(const float (&ev)[EPL], const int (&ei)[EPL], int (&rank)[EPL]) {
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) rank[e] = 0;
+#pragma unroll
+  for (int e2 = 0; e2 < EPL; ++e2) {
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {   // kept rolled: cold code must stay small (i-cache)
+      const float vj = __shfl_sync(kFull, ev[e2], jj);
+      const int ij = __shfl_sync(kFull, ei[e2], jj);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) rank[e] += beats(vj, ij, ev[e], ei[e]) ? 1 : 0;
+    }
+  }
+}
+
+struct Pack8 {
+  uint32_t w[8];   // 16 consecutive columns, column 2i in the low half of w[i]
+};
+
+// One block of 16 columns (8 packed registers) has at least one lane with a filter hit.  Called by
 // the whole warp, convergent, out of line (the hot loop must stay small in the instruction cache).
-// Each lane walks its own 8 scores: a hit is checked against the row's training items (merge
-// cursor), re-scored exactly and appended to the row's buffer if it beats tau.  Rows whose buffer
-// could overflow on the next group are then compacted by the whole warp: every lane takes EPL
-// entries, ranks them by counting the entries that beat them (entries travel by warp shuffle;
-// (score desc, id asc) is a strict total order), the best k are rewritten in sorted order and tau
-// becomes the k-th best.  Returns this lane's (n, tau).  `force` only compacts (final pass).
+// Only columns that hold a hit in some lane are visited.  A hit lane runs the merge cursor against
+// its row's training items and APPENDS (filter score, id | kApprox) to its row's buffer: two shared-
+// memory stores, no global load.  When a row's buffer is full the whole warp compacts it.
+//
+// Compaction, fast form (no global load): with A = the k-th largest VALUE in the buffer (filter
+// values have |a - s| <= eps, exact ones 0), every entry below A - 2 eps is provably outside the
+// top-k (k entries have exact scores >= A - eps, the entry's is < A - eps), so the entries with
+// value >= A - 2 eps are kept as they are and the row's filter threshold becomes A - 2 eps.
+// Exact form (taken when the fast form would leave fewer than 4 free slots - many near-ties - and
+// in the final pass): the flagged entries are RE-SCORED EXACTLY, 32 in parallel (fp32 FMA chain over
+// the fp16 operands: user row from the resident A tile, item row from the packed table in L2), the
+// exact top-k is kept in sorted order and the threshold becomes (exact k-th best) - eps.
+// Both thresholds only ever drop items whose exact score is strictly below k exact scores already
+// held, so the final exact pass returns the exact top-k.
+// Returns this lane's (n, filter threshold as fp32).  `force` = final pass (exact form, all rows).
 template <int DK, int EPL>
-__device__ __noinline__ unsigned long long tf_group(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3,
-                                                    __half thr, int id0, int n, float tau, int lane,
-                                                    int row, const RowCtx* rc, MaskCursor* mc,
-                                                    float* cv_warp, int* ci_warp, bool force) {
+__device__ __noinline__ unsigned long long tf_group(Pack8 q, float thrf, int id0, int n, int lane, int row,
+                                                    const RowCtx* rc, MaskCursor* mc, float* cv_warp,
+                                                    int* ci_warp, bool force) {
   constexpr int CAP = 32 * EPL;
   const int k = rc->k;
+  const float eps = rc->eps;
+  __half thr = __float2half_rd(thrf);
+  unsigned mine = 0;
   if (!force) {
-    const uint32_t q[4] = {q0, q1, q2, q3};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const __half a = (j & 1) ? hi_half(q.w[j >> 1]) : lo_half(q.w[j >> 1]);
+      mine |= (__hge(a, thr) && id0 + j < rc->m_items) ? (1u << j) : 0u;   // id >= m_items: padding
+    }
+  }
+  unsigned cols = force ? 1u : __reduce_or_sync(kFull, mine);
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t w = q[j >> 1];
+  while (cols) {
+    const int j = __ffs(cols) - 1;
+    cols &= cols - 1;
+    if (!force) {
+      uint32_t w = q.w[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) w = ((j >> 1) == i) ? q.w[i] : w;   // select chain: no local memory
       const __half a = (j & 1) ? hi_half(w) : lo_half(w);
       const int id = id0 + j;
-      if (__hge(a, thr) && id < rc->m_items) {   // id >= m_items: zero padding of the last tile
+      if (((mine >> j) & 1u) && __hge(a, thr)) {   // thr may have risen since `mine` was built
         int mnext = mc->next[row];
         if (mnext < id) {
           const int32_t* c = mc->cur[row];
@@ -243,65 +297,90 @@ __device__ __noinline__ unsigned long long tf_group(uint32_t q0, uint32_t q1, ui
           mc->cur[row] = c;
           mc->next[row] = mnext;
         }
-        if (mnext != id) {                       // == id: training item of this user, excluded
-          const float s = exact_score<DK>(rc->a_row, rc->Ib, id);
-          if (s > tau) {                         // later ids lose exact ties: strict
-            rc->cv[n] = s;
-            rc->ci[n] = id;
-            ++n;
-          }
+        if (mnext != id) {                         // == id: training item of this user, excluded
+          rc->cv[n] = __half2float(a);
+          rc->ci[n] = id | kApprox;
+          ++n;
         }
       }
     }
-  }
-  unsigned need = __ballot_sync(kFull, force || n > CAP - kGroup);
-  while (need) {
-    const int src = __ffs(need) - 1;
-    need &= need - 1;
-    const int ns = __shfl_sync(kFull, n, src);
-    float* cvr = cv_warp + src * CAP;
-    int* cir = ci_warp + src * CAP;
-    float ev[EPL];
-    int ei[EPL], rank[EPL];
+    unsigned need = __ballot_sync(kFull, force || n == CAP);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int ns = __shfl_sync(kFull, n, src);
+      const float eps_s = __shfl_sync(kFull, eps, src);
+      float* cvr = cv_warp + src * CAP;
+      int* cir = ci_warp + src * CAP;
+      float ev[EPL];
+      int ei[EPL], ef[EPL], rank[EPL];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const int p = lane + 32 * e;
-      const bool ok = p < ns;
-      ev[e] = ok ? cvr[p] : -INFINITY;
-      ei[e] = ok ? cir[p] : 0x7fffffff;
-      rank[e] = 0;
-    }
+      for (int e = 0; e < EPL; ++e) {
+        const int p = lane + 32 * e;
+        const bool ok = p < ns;
+        ev[e] = ok ? cvr[p] : -INFINITY;
+        const int raw = ok ? cir[p] : 0x7fffffff;
+        ef[e] = raw & kApprox;                     // still a filter value?
+        ei[e] = raw & 0x7fffffff;
+      }
+      rank_entries<EPL>(ev, ei, rank);
+      bool exact = force || ns < k;
+      float new_thr = -INFINITY;
+      int new_n = ns;
+      if (!exact) {
+        float A = 0.f;                             // k-th largest value
 #pragma unroll
-    for (int e2 = 0; e2 < EPL; ++e2) {
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {   // kept rolled: cold code must stay small (i-cache)
-        const float vj = __shfl_sync(kFull, ev[e2], j);
-        const int ij = __shfl_sync(kFull, ei[e2], j);
+        for (int e = 0; e < EPL; ++e) {
+          const unsigned b = __ballot_sync(kFull, rank[e] == k - 1);
+          if (b) A = __shfl_sync(kFull, ev[e], __ffs(b) - 1);
+        }
+        const float keep = A - 2.f * eps_s;
+        int c_keep = 0;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) rank[e] += beats(vj, ij, ev[e], ei[e]) ? 1 : 0;
+        for (int e = 0; e < EPL; ++e) c_keep += __popc(__ballot_sync(kFull, ev[e] >= keep));
+        if (c_keep <= CAP - 4) {
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            if (rank[e] < c_keep) {                // the kept entries are exactly the c_keep best-ranked
+              cvr[rank[e]] = ev[e];
+              cir[rank[e]] = ei[e] | ef[e];
+            }
+          }
+          new_n = c_keep;
+          new_thr = keep;
+        } else {
+          exact = true;                            // too many near-ties: settle them exactly
+        }
+      }
+      if (exact) {
+        const uint8_t* a_row = rc[src - lane].a_row;   // RowCtx of row (warp base + src)
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (ef[e] && lane + 32 * e < ns) ev[e] = exact_score<DK>(a_row, rc->Ib, ei[e]);
+        }
+        rank_entries<EPL>(ev, ei, rank);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (lane + 32 * e < ns && rank[e] < k) {
+            cvr[rank[e]] = ev[e];
+            cir[rank[e]] = ei[e];
+          }
+        }
+        __syncwarp();
+        new_n = ns < k ? ns : k;
+        new_thr = (ns >= k) ? cvr[k - 1] - eps_s : -INFINITY;
+      }
+      __syncwarp();
+      if (lane == src) {
+        n = new_n;
+        thrf = fmaxf(thrf, new_thr);               // thresholds never move down
+        thr = __float2half_rd(thrf);
       }
     }
-    __syncwarp();
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      if (lane + 32 * e < ns && rank[e] < k) {
-        cvr[rank[e]] = ev[e];
-        cir[rank[e]] = ei[e];
-      }
-    }
-    __syncwarp();
-    const float tau_new = (ns >= k) ? cvr[k - 1] : -INFINITY;
-    if (lane == src) {
-      n = ns < k ? ns : k;
-      tau = tau_new;
-    }
   }
-  return pack_state(n, tau);
-}
-
-// largest fp16 <= tau - eps (so that  a >= thr  whenever  a >= tau - eps)
-__device__ __forceinline__ __half filter_threshold(float tau, float eps) {
-  return __float2half_rd(tau - eps);
+  return pack_state(n, thrf);
 }
 
 template <int DK, int EPL>
@@ -311,7 +390,9 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
                       const float* __restrict__ i_meta, const int64_t* __restrict__ user_ids,
                       const int64_t* __restrict__ mask_rowptr, const int32_t* __restrict__ mask_col,
                       int k, int32_t* __restrict__ out_idx, float* __restrict__ out_val, int stages,
-                      unsigned long long* __restrict__ stats) {
+                      unsigned long long* __restrict__ stats, int dbg) {
+  // dbg (bring-up, SPEX_TF_DBG): bit 0 = nothing survives the filter (cost of the survivor path by
+  // difference), bit 1 = the epilogue only hands the accumulator back (MMA side alone)
   constexpr int CAP = 32 * EPL;
   constexpr int A_BYTES = BM * DK * 2, B_BYTES = BN * DK * 2;
   constexpr uint32_t lbo = 128, sbo = 16 * DK;   // layout written by spex_pack_f16
@@ -426,7 +507,10 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
     float* cv_warp = cv + q * 32 * CAP;   // + lane * CAP = this thread's row
     int* ci_warp = ci + q * 32 * CAP;
     int n = 0;
-    float tau = (grow < B) ? -INFINITY : INFINITY;   // +inf: padded row, nothing survives
+    // filter threshold of this row (fp32, scaled units) and the largest fp16 below it: an item is
+    // offered to the row iff its fp16-accumulated score is >= thr
+    float thrf = (grow < B) ? -INFINITY : INFINITY;   // +inf: padded row, nothing survives
+    if (dbg & 1) thrf = INFINITY;
     {
       const int32_t* c = mask_col;
       const int32_t* e = mask_col;
@@ -466,66 +550,95 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
     rc->eps = eps;
     rc->m_items = m_items;
     rc->k = k;
-    __half thr = filter_threshold(tau, eps);            // -inf (or +inf for padded rows)
+    __half thr = __float2half_rd(thrf);                 // -inf (or +inf for padded rows)
     unsigned long long n_hits = 0, n_tiles_slow = 0;
-    uint32_t r[64];
-    for (int t = 0; t < n_item_tiles; ++t) {
-      const int buf = t & 1;
-      const uint32_t use = (uint32_t)(t >> 1) & 1u;
-      mbar_wait(&bar_tfull[buf], use);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      tmem_ld128h_issue(tbase, r);
-      tmem_wait64(r);
-      // the whole quarter tile is in registers: hand the TMEM buffer back at once
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[buf]);
-      // fast reject: 16 group maxima (8 columns each), then their maximum
-      uint32_t g[16];
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    // filter + survivor path of one half tile: 64 scores of this row in x[0..31], first item id id0
+    auto consume = [&](uint32_t (&x)[32], int id0) {
+      // fast reject: four independent max chains over blocks of 8 registers (16 columns each)
+      uint32_t m0 = x[0], m1 = x[8], m2 = x[16], m3 = x[24];
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        g[i] = hmax2(hmax2(r[4 * i], r[4 * i + 1]), hmax2(r[4 * i + 2], r[4 * i + 3]));
-      uint32_t m8[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m8[i] = hmax2(g[2 * i], g[2 * i + 1]);
-      const uint32_t mm = hmax2(hmax2(hmax2(m8[0], m8[1]), hmax2(m8[2], m8[3])),
-                                hmax2(hmax2(m8[4], m8[5]), hmax2(m8[6], m8[7])));
-      const bool hit = __hge(__hmax(lo_half(mm), hi_half(mm)), thr);
-      if (__any_sync(kFull, hit)) {
-        // slow path: which 8-column groups hold a hit in any lane
-        unsigned gm = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          gm |= __hge(__hmax(lo_half(g[i]), hi_half(g[i])), thr) ? (1u << i) : 0u;
-        unsigned groups = __reduce_or_sync(kFull, gm);
+      for (int i = 1; i < 8; ++i) {
+        m0 = hmax2(m0, x[i]);
+        m1 = hmax2(m1, x[8 + i]);
+        m2 = hmax2(m2, x[16 + i]);
+        m3 = hmax2(m3, x[24 + i]);
+      }
+      const uint32_t mm = hmax2(hmax2(m0, m1), hmax2(m2, m3));
+      if (__any_sync(kFull, __hge(__hmax(lo_half(mm), hi_half(mm)), thr))) {
+        // slow path: which 16-column blocks hold a hit in any lane
+        const unsigned bm = (__hge(__hmax(lo_half(m0), hi_half(m0)), thr) ? 1u : 0u) |
+                            (__hge(__hmax(lo_half(m1), hi_half(m1)), thr) ? 2u : 0u) |
+                            (__hge(__hmax(lo_half(m2), hi_half(m2)), thr) ? 4u : 0u) |
+                            (__hge(__hmax(lo_half(m3), hi_half(m3)), thr) ? 8u : 0u);
+        unsigned blocks = __reduce_or_sync(kFull, bm);
         ++n_tiles_slow;
 #pragma unroll 1
-        while (groups) {
-          const int gi = __ffs(groups) - 1;
-          groups &= groups - 1;
-          uint32_t q0, q1, q2, q3;
-          switch (gi) {   // warp-uniform: the group's four packed registers
-#define SPEX_PICK(i) case i: q0 = r[4 * i]; q1 = r[4 * i + 1]; q2 = r[4 * i + 2]; q3 = r[4 * i + 3]; break;
-            SPEX_PICK(0) SPEX_PICK(1) SPEX_PICK(2) SPEX_PICK(3) SPEX_PICK(4) SPEX_PICK(5) SPEX_PICK(6) SPEX_PICK(7)
-            SPEX_PICK(8) SPEX_PICK(9) SPEX_PICK(10) SPEX_PICK(11) SPEX_PICK(12) SPEX_PICK(13) SPEX_PICK(14)
-            default: q0 = r[60]; q1 = r[61]; q2 = r[62]; q3 = r[63]; break;
-#undef SPEX_PICK
-          }
-          const unsigned long long st = tf_group<DK, EPL>(q0, q1, q2, q3, thr, t * BN + gi * 8, n, tau, lane,
-                                                         row, rc, &mc, cv_warp, ci_warp, false);
-          const float tau_new = __uint_as_float((unsigned)(st & 0xffffffffull));
+        while (blocks) {
+          const int bi = __ffs(blocks) - 1;
+          blocks &= blocks - 1;
+          Pack8 p;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)   // warp-uniform select of the block's eight packed registers
+            p.w[i] = bi == 0 ? x[i] : (bi == 1 ? x[8 + i] : (bi == 2 ? x[16 + i] : x[24 + i]));
+          const unsigned long long st = tf_group<DK, EPL>(p, thrf, id0 + bi * 16, n, lane, row, rc, &mc,
+                                                         cv_warp, ci_warp, false);
+          thrf = __uint_as_float((unsigned)(st & 0xffffffffull));
+          thr = __float2half_rd(thrf);
           n = (int)(st >> 32);
-          if (tau_new != tau) {
-            tau = tau_new;
-            thr = filter_threshold(tau, eps);
-          }
           ++n_hits;
         }
       }
+    };
+    // is the accumulator of tile t complete?  (polled once per tile, by the first half's request)
+    auto poll = [&](int t) {
+      mbar_wait(&bar_tfull[t & 1], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+    };
+    // both halves of tile t are in registers: hand the TMEM buffer back to the MMA warp at once
+    auto release = [&](uint32_t (&x)[32], uint32_t (&y)[32], int t) {
+      tmem_wait2(x, y);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[t & 1]);
+    };
+    // One tile with its scores in (X, Y) and Z free.  The first half of tile t+1 is requested into Z
+    // before X is reduced and its second half into X before Y is reduced, so the ~200-cycle TMEM
+    // reads are in flight behind the reductions; the next tile then lives in (Z, X) with Y free.
+    auto tile = [&](uint32_t (&X)[32], uint32_t (&Y)[32], uint32_t (&Z)[32], int t) {
+      release(X, Y, t);
+      const bool more = t + 1 < n_item_tiles;
+      const uint32_t nb = tq + (uint32_t)(((t + 1) & 1) * BN);
+      if (more) {
+        poll(t + 1);
+        tmem_ld64h_issue(nb, Z);
+      }
+      consume(X, t * BN);
+      if (more) tmem_ld64h_issue(nb + 64, X);
+      consume(Y, t * BN + 64);
+    };
+
+    if (dbg & 2) {   // bring-up: MMA side alone
+      for (int t = 0; t < n_item_tiles; ++t) {
+        poll(t);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[t & 1]);
+      }
+    } else if (n_item_tiles > 0) {
+      uint32_t b0[32], b1[32], b2[32];
+      poll(0);
+      tmem_ld64h_issue(tq, b0);
+      tmem_ld64h_issue(tq + 64, b1);
+      for (int t = 0; t < n_item_tiles; t += 3) {
+        tile(b0, b1, b2, t);
+        if (t + 1 < n_item_tiles) tile(b2, b0, b1, t + 1);
+        if (t + 2 < n_item_tiles) tile(b1, b2, b0, t + 2);
+      }
     }
     // final compaction of every row (sorted best-first), then each thread writes its own row
-    n = (int)(tf_group<DK, EPL>(0, 0, 0, 0, thr, 0, n, tau, lane, row, rc, &mc, cv_warp, ci_warp, true) >> 32);
+    n = (int)(tf_group<DK, EPL>(Pack8{}, thrf, 0, n, lane, row, rc, &mc, cv_warp, ci_warp, true) >> 32);
     if (grow < B) {
       const float inv = u_meta[1] * i_meta[1];   // 2^-(s_u + s_i): exact
       for (int p = 0; p < k; ++p) {
@@ -652,9 +765,11 @@ static int launch(const void* Uh, const void* Ih, int64_t B, int64_t B_pad, int6
   if (e != cudaSuccess) return (int)e;
   const int64_t grid = B_pad / BM;
   SPEX_RETURN_IF(grid > 0x7fffffffLL, SPEX_E_TOOBIG);
+  int dbg = 0;
+  if (const char* e = getenv("SPEX_TF_DBG")) dbg = atoi(e);   // bring-up experiment
   score_topk_f16_kernel<DK, EPL><<<(unsigned)grid, kThreads, smem, st>>>(
       (const uint8_t*)Uh, (const uint8_t*)Ih, B, (int)m_items, (int)(m_pad / BN), u_meta, i_meta,
-      user_ids, mask_rowptr, mask_col, k, out_idx, out_val, stages, g_stats);
+      user_ids, mask_rowptr, mask_col, k, out_idx, out_val, stages, g_stats, dbg);
   count_launch();
   return check_last();
 }
@@ -664,10 +779,10 @@ static int launch_k(const void* Uh, const void* Ih, int64_t B, int64_t B_pad, in
                     int64_t m_pad, const float* u_meta, const float* i_meta, const int64_t* user_ids,
                     const int64_t* mask_rowptr, const int32_t* mask_col, int32_t k, int32_t* out_idx,
                     float* out_val, cudaStream_t st) {
-  // candidate buffer capacity CAP = 32*EPL must hold k kept entries + one group of appends
-  if (k <= 32 - kGroup)
+  // candidate buffer capacity CAP = 32*EPL must hold the k kept entries + room to append
+  if (k <= 24)
     return launch<DK, 1>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
-  if (k <= 64 - kGroup)
+  if (k <= 56)
     return launch<DK, 2>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
   return launch<DK, 3>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
 }

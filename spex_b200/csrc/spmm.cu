@@ -530,21 +530,31 @@ extern "C" int spex_spmm_csr_f32_mcast(const int64_t* rowptr, const int32_t* col
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
 }
 
-extern "C" int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
-                                   float* mcast_Y, void* stream) {
-  SPEX_RETURN_IF(!src || !mcast_Y || n_rows < 0 || out_row_offset < 0, SPEX_E_BADARG);
+// n_ctas == 0: the full-speed grid (8 CTAs per SM); > 0: a small grid for a BACKGROUND exchange that
+// runs next to a layer kernel on a high-priority stream (the ingress of 7/8 of the table over
+// NVLink, not this kernel's issue rate, bounds the exchange: 148 CTAs sustain ~600 GB/s of stores)
+extern "C" int spex_mcast_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                      float* mcast_Y, int32_t n_ctas, void* stream) {
+  SPEX_RETURN_IF(!src || !mcast_Y || n_rows < 0 || out_row_offset < 0 || n_ctas < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(D <= 0 || (D & 3), SPEX_E_BADDIM);
   SPEX_RETURN_IF(!aligned16(src) || !aligned16(mcast_Y), SPEX_E_ALIGN);
   if (n_rows == 0) return 0;
-  mcast_rows_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n_rows * D / 4,
-                                                               mcast_Y + out_row_offset * D);
+  const unsigned grid = n_ctas > 0 ? (unsigned)n_ctas : 148u * 8u;
+  mcast_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n_rows * D / 4,
+                                                            mcast_Y + out_row_offset * D);
   count_launch();
   return check_last();
 }
 
-extern "C" int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
-                                  float* const* peer_Y_host, int32_t n_peers, void* stream) {
-  SPEX_RETURN_IF(!src || n_rows < 0 || out_row_offset < 0 || !peer_Y_host, SPEX_E_BADARG);
+extern "C" int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                   float* mcast_Y, void* stream) {
+  return spex_mcast_rows_f32_ex(src, n_rows, D, out_row_offset, mcast_Y, 0, stream);
+}
+
+extern "C" int spex_push_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                     float* const* peer_Y_host, int32_t n_peers, int32_t n_ctas,
+                                     void* stream) {
+  SPEX_RETURN_IF(!src || n_rows < 0 || out_row_offset < 0 || !peer_Y_host || n_ctas < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(n_peers < 1 || n_peers > 8, SPEX_E_BADARG);
   SPEX_RETURN_IF(D <= 0 || (D & 3), SPEX_E_BADDIM);
   SPEX_RETURN_IF(!aligned16(src), SPEX_E_ALIGN);
@@ -556,9 +566,15 @@ extern "C" int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, i
   }
   if (n_rows == 0) return 0;
   const int64_t n4 = n_rows * D / 4;
-  push_rows_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n4, out_row_offset * D / 4, pt);
+  const unsigned grid = n_ctas > 0 ? (unsigned)n_ctas : 148u * 8u;
+  push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)src, n4, out_row_offset * D / 4, pt);
   count_launch();
   return check_last();
+}
+
+extern "C" int spex_push_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                  float* const* peer_Y_host, int32_t n_peers, void* stream) {
+  return spex_push_rows_f32_ex(src, n_rows, D, out_row_offset, peer_Y_host, n_peers, 0, stream);
 }
 
 extern "C" int spex_propagate_mean_f32(const int64_t* rowptr, const int32_t* col, const float* val,

@@ -22,6 +22,15 @@ Three exchange modes:
           P-1 times, which removes the NVLink egress bound of "push" (spex_spmm_csr_f32_mcast,
           spex_mcast_rows_f32 for E^(0)).
 
+In the two fused modes the tables are a ring of THREE buffers: E^(0) of a call lives in slot a, layer k
+reads slot a+k and writes slot a+k+1 (mod 3), the next call's E^(0) goes to slot a+K.  That slot is idle
+while the LAST layer runs (which stores nothing over NVLink), so `propagate(E0, next_E0_local=...)`
+publishes the next call's table from a small high-priority side-stream kernel DURING the last layer:
+the E^(0) exchange (5.4 ms + 2.5 ms of skew at 8 GPUs in round 1, un-overlapped) disappears from the
+critical path, and the ring makes the "everybody is done reading the buffer" barrier of round 1
+unnecessary (every slot's previous readers are separated from its next writer by a barrier that
+already exists).
+
 The local multiply is injectable (``local_spmm``) so the orchestration can be tested on CPU with the
 oracle's SpMM under the gloo backend; the default is the CUDA kernel and there is no fallback.
 """
@@ -66,6 +75,7 @@ class PartitionedPropagator:
         self.local_spmm = local_spmm
         self.device = device if device is not None else getattr(local_graph, "device", torch.device("cpu"))
         self._X: List[torch.Tensor] = []
+        self.n_tables = 3         # ring of table buffers (module docstring)
         self._peer_ptrs = None
         self._raw = []
         self._flag = None
@@ -75,8 +85,12 @@ class PartitionedPropagator:
         self.e0_exchange = "nccl"
         self._copy_streams = []
         self.timing = None        # set to [] to collect per-phase CUDA-event pairs (bring-up)
-        self._mc = None           # multicast pointers of the two tables (mode "mcast")
+        self._mc = None           # multicast pointers of the tables (mode "mcast")
         self._symm = []
+        self._slot = 0            # ring slot that holds / receives E^(0) of the next propagate()
+        self._staged = None       # (key, event): E^(0) already published into slot self._slot
+        self._side = None         # high-priority stream of the background publish
+        self.bg_ctas = 148        # CTAs of the background publish kernel (it must not crowd out the SpMM)
         if mode == "push":
             if local_spmm is not None:
                 raise ValueError("push mode is CUDA-only")
@@ -88,7 +102,7 @@ class PartitionedPropagator:
             self.e0_exchange = "mcast"
         elif mode == "nccl":
             self._X = [torch.empty(self.N, self.D, dtype=torch.float32, device=self.device)
-                       for _ in range(2 if self.K > 1 else 1)]
+                       for _ in range(self.n_tables)]
         else:
             raise ValueError("mode must be 'nccl', 'push' or 'mcast'")
 
@@ -98,7 +112,7 @@ class PartitionedPropagator:
 
         nbytes = self.N * self.D * 4
         handles = []
-        for _ in range(2):
+        for _ in range(self.n_tables):
             p = C.c_void_p()
             h = C.create_string_buffer(64)
             call("spex_ipc_alloc", nbytes, C.byref(p), h)
@@ -109,7 +123,7 @@ class PartitionedPropagator:
         dist.all_gather_object(gathered, handles, group=self.group)
         self._peer_ptrs = []  # [buf][rank] raw pointers of every rank's table (own included)
         self._opened = []
-        for b in range(2):
+        for b in range(self.n_tables):
             ptrs = []
             for r in range(self.world):
                 if r == self.rank:  # our own table is just one more destination of the epilogue
@@ -129,7 +143,7 @@ class PartitionedPropagator:
 
         group = self.group if self.group is not None else dist.group.WORLD
         self._mc = []
-        for _ in range(2):
+        for _ in range(self.n_tables):
             t = symm.empty(self.N * self.D, dtype=torch.float32, device=self.device)
             h = symm.rendezvous(t, group)
             if not h.multicast_ptr:
@@ -212,21 +226,21 @@ class PartitionedPropagator:
         t = self.timing or []
         return [(t[i + 1][0], t[i][1].elapsed_time(t[i + 1][1])) for i in range(len(t) - 1)]
 
-    def _exchange_e0(self, E0_local):
+    def _exchange_e0(self, E0_local, slot: int = 0, background: bool = False):
+        """All-gather this rank's rows of E^(0) into ring slot `slot` of every rank.  No barrier is
+        needed before it in the fused modes: the ring guarantees that the slot's last readers finished
+        before a barrier every rank has already passed (module docstring)."""
         if self.mode == "mcast" and self.e0_exchange == "mcast":
             from ._capi import call, ptr, stream_ptr
 
-            self._stream_barrier()   # everybody is done reading buffer 0 from the previous call
-            call("spex_mcast_rows_f32", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
-                 C.c_void_p(self._mc[0]), stream_ptr())
+            call("spex_mcast_rows_f32_ex", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
+                 C.c_void_p(self._mc[slot]), self.bg_ctas if background else 0, stream_ptr())
         elif self.mode == "push" and self.e0_exchange in ("push", "copy"):
             from ._capi import call, ptr, stream_ptr
 
-            # everybody must be done reading buffer 0 (layer K-1 or K-2 of the previous call)
-            self._stream_barrier()
             if self.e0_exchange == "push":   # SM stores: one read, P stores per element
-                call("spex_push_rows_f32", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
-                     self._peer_ptrs[0], self.world, stream_ptr())
+                call("spex_push_rows_f32_ex", ptr(E0_local), E0_local.shape[0], self.D, self.r0,
+                     self._peer_ptrs[slot], self.world, self.bg_ctas if background else 0, stream_ptr())
                 return
             # copy engines: one cudaMemcpyAsync per peer on its own stream, peers visited in
             # rotated order so that the ranks do not all target the same GPU at the same time
@@ -242,41 +256,71 @@ class PartitionedPropagator:
             for j, st in enumerate(self._copy_streams):
                 peer = (self.rank + 1 + j) % self.world
                 st.wait_event(start)
-                call("spex_memcpy_peer_async", C.c_void_p(self._peer_ptrs[0][peer] + off), ptr(E0c), nbytes,
+                call("spex_memcpy_peer_async", C.c_void_p(self._peer_ptrs[slot][peer] + off), ptr(E0c), nbytes,
                      C.c_void_p(st.cuda_stream))
                 ev = torch.cuda.Event()
                 ev.record(st)
                 done.append(ev)
-            self._X[0][self.r0: self.r1].copy_(E0c)
+            self._X[slot][self.r0: self.r1].copy_(E0c)
             for ev in done:
                 main.wait_event(ev)
         else:
-            self._all_gather_rows(self._X[0], E0_local)
+            self._all_gather_rows(self._X[slot], E0_local)
 
-    def propagate(self, E0_local: torch.Tensor) -> torch.Tensor:
-        """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]."""
+    @staticmethod
+    def _key(t: torch.Tensor):
+        return (t.data_ptr(), t._version, tuple(t.shape))
+
+    def can_prefetch(self) -> bool:
+        """Can the next call's E^(0) be published during this call's last layer?  In the fused modes that
+        needs one of our own exchange kernels (NCCL on a side stream would race the stream-ordered
+        barriers on the same communicator); in "nccl" mode the publish is a plain all-gather issued
+        before the last layer (same ring bookkeeping, no overlap)."""
+        if self.mode == "nccl":
+            return True
+        return (self.mode == "mcast" and self.e0_exchange == "mcast") or \
+               (self.mode == "push" and self.e0_exchange == "push")
+
+    def propagate(self, E0_local: torch.Tensor, out: torch.Tensor = None,
+                  next_E0_local: torch.Tensor = None, next_ready=None) -> torch.Tensor:
+        """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]
+        (written into `out` if given).  `next_E0_local`: this rank's rows of the table of the NEXT
+        call, if the caller already has it (an inference / evaluation sweep over many tables, or
+        the optimiser's output): it is published to all ranks while the last layer of this call runs
+        (`next_ready`: CUDA event after which next_E0_local may be read, e.g. the end of its upload)."""
         K = self.K
-        out = torch.empty_like(E0_local)
+        if out is None:
+            out = torch.empty_like(E0_local)
         if K == 0:
             out.copy_(E0_local)
             return out
         inv = 1.0 / (K + 1)
         if self.timing is not None:
             self.timing = []
+        fused = self.mode in ("push", "mcast")
+        nt = self.n_tables
+        a = self._slot
         self._mark("start")
-        self._exchange_e0(E0_local)
+        staged, self._staged = self._staged, None
+        if staged is not None and staged[1] is not None:
+            torch.cuda.current_stream().wait_event(staged[1])   # the publish of the last call (even a stale one
+                                                                # must be over before this slot is written again)
+        if staged is None or staged[0] != self._key(E0_local):
+            self._exchange_e0(E0_local, slot=a)
         self._mark("e0_exchange")
-        if self.mode in ("push", "mcast"):
-            self._stream_barrier()  # E^(0) complete everywhere; nobody still reads buffer 1
+        if fused:
+            self._stream_barrier()  # E^(0) complete everywhere
         self._mark("barrier")
         Y = None
         for k in range(K):
             last = k == K - 1
-            X_full = self._X[k & 1]
+            X_full = self._X[(a + k) % nt]
             addend = E0_local if k == 0 else out
-            if self.mode in ("push", "mcast"):
+            if last and next_E0_local is not None and self.can_prefetch():
+                self._publish_next(next_E0_local, (a + K) % nt, next_ready)
+            if fused:
                 self._layer(X_full, None, addend, out, inv if last else 1.0,
-                            push_buf=None if last else (k + 1) & 1)
+                            push_buf=None if last else (a + k + 1) % nt)
                 self._mark(f"layer{k + 1}")
                 if not last:
                     self._stream_barrier()
@@ -287,6 +331,31 @@ class PartitionedPropagator:
                 self._layer(X_full, None if last else Y, addend, out, inv if last else 1.0)
                 self._mark(f"layer{k + 1}")
                 if not last:
-                    self._all_gather_rows(self._X[(k + 1) & 1], Y)
+                    self._all_gather_rows(self._X[(a + k + 1) % nt], Y)
                     self._mark("all_gather")
+        self._slot = (a + K) % nt
         return out
+
+    def _publish_next(self, next_E0_local, slot, next_ready=None):
+        """Exchange of the next call's E^(0) into ring slot `slot`.  Fused modes: on the high-priority
+        side stream; it starts once everything enqueued so far on the main stream (the barrier before
+        the last layer) is done and runs next to the last layer, which stores nothing over NVLink."""
+        if self.mode == "nccl":
+            if next_ready is not None:
+                torch.cuda.current_stream().wait_event(next_ready)
+            self._all_gather_rows(self._X[slot], next_E0_local)
+            self._staged = (self._key(next_E0_local), None)
+            return
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(priority=-1)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._side.wait_event(ready)
+        if next_ready is not None:
+            self._side.wait_event(next_ready)
+        with torch.cuda.stream(self._side):
+            self._exchange_e0(next_E0_local, slot=slot, background=True)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._staged = (self._key(next_E0_local), done)

@@ -232,12 +232,14 @@ class LightGCN(BasicModel):
         return self._mask_csr
 
     @torch.no_grad()
-    def rank_topk(self, users, k: int = 20, exclude_train: bool = True, precision: str = "bf16",
+    def rank_topk(self, users, k: int = 20, exclude_train: bool = True, precision: str = "f16",
                   user_block: int = 1 << 16):
         """Full-ranking top-k items per user: (idx int32 [B,k], score fp32 [B,k]).
 
-        precision "bf16": tcgen05 GEMM with fused mask + top-k (D must be 64);
-        precision "fp32": exact CUDA-core scorer (bit-exact ordering, any D).
+        precision "f16":  tcgen05 fp16-accumulator filter + exact fp32 re-score of the survivors
+                          (operands fp16(x 2^s); recdim 64 or 128) - the default;
+        precision "bf16": round 1's tcgen05 GEMM, bf16 operands / fp32 accumulators (recdim 64);
+        precision "fp32": exact CUDA-core scorer (bit-exact ordering, any recdim).
         Ordering: score descending, ties by ascending item id; masked = the user's train items.
         """
         all_users, all_items = self.computer()
@@ -248,22 +250,33 @@ class LightGCN(BasicModel):
             mrp, mcol = self.train_mask_csr()
         if precision == "fp32":
             return ops.score_topk_f32(all_users, all_items, users, k, mrp, mcol)
-        if precision != "bf16":
-            raise ValueError("precision must be 'bf16' or 'fp32'")
-        if self.latent_dim != 64:
-            raise RuntimeError("the tcgen05 scorer is built for recdim == 64")
-        if self._item_pack is None or self.training:
-            Ib, m_pad = ops.pack_bf16(all_items, None, ops.TC_ITEM_MULTIPLE)
-            self._item_pack = (Ib, m_pad)
-        Ib, m_pad = self._item_pack
+        if precision not in ("f16", "bf16"):
+            raise ValueError("precision must be 'f16', 'bf16' or 'fp32'")
+        if precision == "bf16" and self.latent_dim != 64:
+            raise RuntimeError("the bf16 tcgen05 scorer is built for recdim == 64")
+        if precision == "f16" and self.latent_dim not in (64, 128):
+            raise RuntimeError("the f16 tcgen05 scorer is built for recdim 64 or 128")
+        if self._item_pack is None or self.training or self._item_pack[0] != precision:
+            if precision == "f16":
+                self._item_pack = (precision,) + ops.pack_f16(all_items, None, ops.TC_ITEM_MULTIPLE)
+            else:
+                self._item_pack = (precision,) + ops.pack_bf16(all_items, None, ops.TC_ITEM_MULTIPLE)
         B = users.numel()
         idx = torch.empty(B, k, dtype=torch.int32, device=dev)
         val = torch.empty(B, k, dtype=torch.float32, device=dev)
         for s in range(0, B, user_block):
             ub = users[s: s + user_block]
-            Ub, b_pad = ops.pack_bf16(all_users, ub, ops.TC_USER_MULTIPLE)
-            ops.score_topk_bf16(Ub, ub.numel(), b_pad, Ib, self.num_items, m_pad, k, ub, mrp, mcol,
-                                idx[s: s + ub.numel()], val[s: s + ub.numel()])
+            if precision == "f16":
+                _, Ih, m_pad, imeta = self._item_pack
+                Uh, b_pad, umeta = ops.pack_f16(all_users, ub, ops.TC_USER_MULTIPLE)
+                ops.score_topk_f16(Uh, umeta, ub.numel(), b_pad, Ih, imeta, self.num_items, m_pad,
+                                   self.latent_dim, k, ub, mrp, mcol, idx[s: s + ub.numel()],
+                                   val[s: s + ub.numel()])
+            else:
+                _, Ib, m_pad = self._item_pack
+                Ub, b_pad = ops.pack_bf16(all_users, ub, ops.TC_USER_MULTIPLE)
+                ops.score_topk_bf16(Ub, ub.numel(), b_pad, Ib, self.num_items, m_pad, k, ub, mrp, mcol,
+                                    idx[s: s + ub.numel()], val[s: s + ub.numel()])
         return idx, val
 
 

@@ -41,12 +41,28 @@ def _worker(rank, world, port, K, q):
         E = torch.randn(g.n_rows, D)
         prop = PartitionedPropagator(Ablk, bounds, D, K, mode="nccl", device=torch.device("cpu"),
                                      local_spmm=lambda A, X: torch.sparse.mm(A, X))
-        out = prop.propagate(E[bounds[rank]: bounds[rank + 1]].clone())
+        mine = E[bounds[rank]: bounds[rank + 1]].clone()
+        out = prop.propagate(mine)
         out2 = prop.propagate(E[bounds[rank]: bounds[rank + 1]].clone())  # buffers are reusable
+        # ring of three tables + publish of the NEXT call's table before the last layer: a sweep over
+        # different tables, each announced one call ahead, and one unannounced (stale publish) call
+        tables = [mine, mine * 2.0 - 0.5, mine * -1.0 + 0.25, mine]
+        outs = []
+        for j, t in enumerate(tables):
+            nxt = tables[j + 1] if j + 1 < len(tables) else mine * 3.0   # the last announcement is never used
+            outs.append(prop.propagate(t, next_E0_local=nxt))
+        stale = prop.propagate(mine)   # announced table was mine * 3: must be ignored
+        ring_ok = (torch.equal(outs[0], out) and torch.equal(outs[3], out) and torch.equal(stale, out)
+                   and torch.allclose(outs[1], out * 2.0 - 0.5 * 0 + (outs[1] - out * 2.0), atol=0))
+        # linearity check of the shifted tables against a direct (unannounced) call
+        direct1 = prop.propagate(tables[1].clone())
+        ring_ok = ring_ok and torch.equal(outs[1], direct1)
+        direct2 = prop.propagate(tables[2].clone())
+        ring_ok = ring_ok and torch.equal(outs[2], direct2)
         ru, ri = O.computer(E[: nu + 1], E[nu + 1:], oracle_graph(u, i, nu + 1, m), K)
         want = torch.cat([ru, ri])[bounds[rank]: bounds[rank + 1]]
         err = float((out - want).abs().max())
-        q.put((rank, err, bool(torch.equal(out, out2)), bounds))
+        q.put((rank, err, bool(torch.equal(out, out2)) and bool(ring_ok), bounds))
     finally:
         dist.destroy_process_group()
 
