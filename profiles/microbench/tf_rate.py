@@ -53,7 +53,7 @@ def main():
 
     Ih, m_pad, imeta = ops.pack_f16(I, None, ops.TC_ITEM_MULTIPLE)
     Uh, b_pad, umeta = ops.pack_f16(U, users, ops.TC_USER_MULTIPLE)
-    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
     _capi.lib.spex_debug_tf_stats.argtypes = [C.c_void_p]
     _capi.lib.spex_debug_tf_stats.restype = None
     _capi.lib.spex_debug_tf_stats(C.c_void_p(stats.data_ptr()))
@@ -64,8 +64,11 @@ def main():
     ms = timed(lambda: ops.score_topk_f16(Uh, umeta, args.users, b_pad, Ih, imeta, args.items, m_pad, args.D, args.k,
                                           None, None, None, idx, val))
     n_warp_tiles = (b_pad // 128) * 4 * (m_pad // 128)
+    nw = (b_pad // 128) * 4
     out["f16"] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1), "slow_tiles_frac": st[0] / n_warp_tiles,
-                  "group_calls_per_warp": st[1] / ((b_pad // 128) * 4)}
+                  "block_calls_per_warp": st[1] / nw, "slow_path_cycles_per_warp": st[2] / nw,
+                  "compactions_per_warp": st[3] / nw, "exact_compactions_per_warp": st[4] / nw,
+                  "compaction_cycles_per_warp": st[5] / nw}
     i16 = idx.clone()
     if args.D == 64:
         Ib, m_pad2 = ops.pack_bf16(I, None, ops.TC_ITEM_MULTIPLE)

@@ -17,12 +17,12 @@
 //     same fp16 operands (four K=16 steps, each rounding a partial sum bounded by sum|u_d v_d| <=
 //     |u||v| to fp16: 4 * 2^-12 with round-to-nearest, 4 * 2^-11 = 2^-9 even with truncation;
 //     measured ~2^-14 |u||v|, profiles/microbench/f16acc_b200.txt);
-//   * an epilogue thread owns one user row.  The 128 scores of its row arrive as two half tiles
-//     (tcgen05.ld.32x32b.x32.pack::16b: 64 columns in 32 registers) rotating through THREE
-//     register sets, so that the TMEM read of the next tile is in flight while the current one is
-//     reduced; the accumulator buffer is handed back to the MMA warp as soon as both halves are
-//     in registers.  31 HMNMX2 + one compare + one vote reject a half tile against the row's
-//     threshold thr;
+//   * an epilogue thread owns one user row: ONE tcgen05.ld.x64.pack::16b brings the 128 scores of
+//     its row into 64 registers, the accumulator buffer is handed back to the MMA warp at once,
+//     63 HMNMX2 + one compare + one vote reject the tile against the row's threshold thr.
+//     (Two software-pipelined variants - two 64-register sets, and three 32-register sets rotating
+//     over half tiles - were built and measured: 1322 / 1282 TF for the filter alone against 1430
+//     for this one; the TMEM read is throughput-, not latency-bound with 8 epilogue warps per SM);
 //   * survivors (a >= thr; ~k ln(m/k) (1 + some %) per row over the whole sweep) pass the merge-
 //     cursor test against the user's training items and are appended, with their filter score and
 //     a flag, to the row's candidate buffer in shared memory (two stores: the survivor path does no
@@ -150,20 +150,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
       "+r"(r[o + 21]), "+r"(r[o + 22]), "+r"(r[o + 23]), "+r"(r[o + 24]), "+r"(r[o + 25]),          \
       "+r"(r[o + 26]), "+r"(r[o + 27]), "+r"(r[o + 28]), "+r"(r[o + 29]), "+r"(r[o + 30]),          \
       "+r"(r[o + 31])
-// tcgen05.ld of 32 lanes x 64 columns of fp16 accumulators into 32 registers, without waiting
-__device__ __forceinline__ void tmem_ld64h_issue(uint32_t taddr, uint32_t (&r)[32]) {
+// tcgen05.ld of 32 lanes x 128 columns of fp16 accumulators into 64 registers (column 2i in the low
+// half of register i), without waiting
+__device__ __forceinline__ void tmem_ld128h_issue(uint32_t taddr, uint32_t (&r)[64]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-      "%26,%27,%28,%29,%30,%31}, [%32];"
-      : SPEX_O32(r, 0)
+      "%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,"
+      "%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : SPEX_O32(r, 0), SPEX_O32(r, 32)
       : "r"(taddr)
       : "memory");
 }
-// wait for the outstanding tcgen05.ld of this thread; the "+r" operands tie the loaded registers of
-// both half tiles to the wait so that no consumer can be scheduled above it
-__device__ __forceinline__ void tmem_wait2(uint32_t (&x)[32], uint32_t (&y)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : SPEX_IO32(x, 0), SPEX_IO32(y, 0) : : "memory");
+// wait for the outstanding tcgen05.ld of this thread; the "+r" operands tie the loaded registers
+// to the wait so that no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_wait64(uint32_t (&r)[64]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SPEX_IO32(r, 0), SPEX_IO32(r, 32) : : "memory");
 }
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -179,17 +181,6 @@ __device__ __forceinline__ __half hi_half(uint32_t x) { return __ushort_as_half(
 struct MaskCursor {
   const int32_t* cur[BM];
   const int32_t* end[BM];
-  int next[BM];                // smallest training item id not yet passed (INT_MAX: none left)
-};
-
-struct RowCtx {
-  const uint8_t* a_row;        // this row's first 16-byte chunk in the resident A tile (generic ptr)
-  const uint8_t* Ib;           // packed item table (global)
-  float* cv;                   // this row's candidate scores  [CAP]
-  int* ci;                     // this row's candidate ids     [CAP]
-  float eps;                   // filter margin of this row (scaled units)
-  int m_items;
-  int k;
 };
 
 __device__ __forceinline__ unsigned long long pack_state(int n, float tau) {
@@ -237,147 +228,104 @@ __device__ __forceinline__ void rank_entries(const float (&ev)[EPL], const int (
   }
 }
 
-struct Pack8 {
-  uint32_t w[8];   // 16 consecutive columns, column 2i in the low half of w[i]
-};
-
-// One block of 16 columns (8 packed registers) has at least one lane with a filter hit.  Called by
-// the whole warp, convergent, out of line (the hot loop must stay small in the instruction cache).
-// Only columns that hold a hit in some lane are visited.  A hit lane runs the merge cursor against
-// its row's training items and APPENDS (filter score, id | kApprox) to its row's buffer: two shared-
-// memory stores, no global load.  When a row's buffer is full the whole warp compacts it.
+// Compaction of the candidate buffers of the rows in `need` (one bit per lane = row of this warp's
+// TMEM lane quarter), by the whole warp, out of line (cold code must not bloat the hot loop).
 //
-// Compaction, fast form (no global load): with A = the k-th largest VALUE in the buffer (filter
-// values have |a - s| <= eps, exact ones 0), every entry below A - 2 eps is provably outside the
-// top-k (k entries have exact scores >= A - eps, the entry's is < A - eps), so the entries with
-// value >= A - 2 eps are kept as they are and the row's filter threshold becomes A - 2 eps.
+// Fast form (no global load): with A = the k-th largest VALUE in the buffer (filter values have
+// |a - s| <= eps, exact ones 0), every entry below A - 2 eps is provably outside the top-k (k entries
+// have exact scores >= A - eps, the entry's is < A - eps), so the entries with value >= A - 2 eps
+// are kept as they are and the row's filter threshold becomes A - 2 eps.
 // Exact form (taken when the fast form would leave fewer than 4 free slots - many near-ties - and
 // in the final pass): the flagged entries are RE-SCORED EXACTLY, 32 in parallel (fp32 FMA chain over
 // the fp16 operands: user row from the resident A tile, item row from the packed table in L2), the
 // exact top-k is kept in sorted order and the threshold becomes (exact k-th best) - eps.
 // Both thresholds only ever drop items whose exact score is strictly below k exact scores already
 // held, so the final exact pass returns the exact top-k.
-// Returns this lane's (n, filter threshold as fp32).  `force` = final pass (exact form, all rows).
+// Returns this lane's (n, filter threshold as fp32).  `force` = final pass (exact form).
 template <int DK, int EPL>
-__device__ __noinline__ unsigned long long tf_group(Pack8 q, float thrf, int id0, int n, int lane, int row,
-                                                    const RowCtx* rc, MaskCursor* mc, float* cv_warp,
-                                                    int* ci_warp, bool force) {
+__device__ __noinline__ unsigned long long tf_compact(unsigned need, int n, float thrf, float eps, int k,
+                                                      int lane, int row0, const uint8_t* sA,
+                                                      const uint8_t* Ib, float* cv_warp, int* ci_warp,
+                                                      bool force, unsigned long long* stats) {
   constexpr int CAP = 32 * EPL;
-  const int k = rc->k;
-  const float eps = rc->eps;
-  __half thr = __float2half_rd(thrf);
-  unsigned mine = 0;
-  if (!force) {
+  while (need) {
+    const long long c0 = stats ? clock64() : 0;
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const int ns = __shfl_sync(kFull, n, src);
+    const float eps_s = __shfl_sync(kFull, eps, src);
+    float* cvr = cv_warp + src * CAP;
+    int* cir = ci_warp + src * CAP;
+    float ev[EPL];
+    int ei[EPL], ef[EPL], rank[EPL];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const __half a = (j & 1) ? hi_half(q.w[j >> 1]) : lo_half(q.w[j >> 1]);
-      mine |= (__hge(a, thr) && id0 + j < rc->m_items) ? (1u << j) : 0u;   // id >= m_items: padding
+    for (int e = 0; e < EPL; ++e) {
+      const int p = lane + 32 * e;
+      const bool ok = p < ns;
+      ev[e] = ok ? cvr[p] : -INFINITY;
+      const int raw = ok ? cir[p] : 0x7fffffff;
+      ef[e] = raw & kApprox;                     // still a filter value?
+      ei[e] = raw & 0x7fffffff;
     }
-  }
-  unsigned cols = force ? 1u : __reduce_or_sync(kFull, mine);
-#pragma unroll 1
-  while (cols) {
-    const int j = __ffs(cols) - 1;
-    cols &= cols - 1;
-    if (!force) {
-      uint32_t w = q.w[0];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) w = ((j >> 1) == i) ? q.w[i] : w;   // select chain: no local memory
-      const __half a = (j & 1) ? hi_half(w) : lo_half(w);
-      const int id = id0 + j;
-      if (((mine >> j) & 1u) && __hge(a, thr)) {   // thr may have risen since `mine` was built
-        int mnext = mc->next[row];
-        if (mnext < id) {
-          const int32_t* c = mc->cur[row];
-          const int32_t* e = mc->end[row];
-          do {
-            ++c;
-            mnext = (c < e) ? __ldg(c) : 0x7fffffff;
-          } while (mnext < id);
-          mc->cur[row] = c;
-          mc->next[row] = mnext;
-        }
-        if (mnext != id) {                         // == id: training item of this user, excluded
-          rc->cv[n] = __half2float(a);
-          rc->ci[n] = id | kApprox;
-          ++n;
-        }
-      }
-    }
-    unsigned need = __ballot_sync(kFull, force || n == CAP);
-    while (need) {
-      const int src = __ffs(need) - 1;
-      need &= need - 1;
-      const int ns = __shfl_sync(kFull, n, src);
-      const float eps_s = __shfl_sync(kFull, eps, src);
-      float* cvr = cv_warp + src * CAP;
-      int* cir = ci_warp + src * CAP;
-      float ev[EPL];
-      int ei[EPL], ef[EPL], rank[EPL];
+    rank_entries<EPL>(ev, ei, rank);
+    bool exact = force || ns < k;
+    float new_thr = -INFINITY;
+    int new_n = ns;
+    if (!exact) {
+      float A = 0.f;                             // k-th largest value
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
-        const int p = lane + 32 * e;
-        const bool ok = p < ns;
-        ev[e] = ok ? cvr[p] : -INFINITY;
-        const int raw = ok ? cir[p] : 0x7fffffff;
-        ef[e] = raw & kApprox;                     // still a filter value?
-        ei[e] = raw & 0x7fffffff;
+        const unsigned b = __ballot_sync(kFull, rank[e] == k - 1);
+        if (b) A = __shfl_sync(kFull, ev[e], __ffs(b) - 1);
+      }
+      const float keep = A - 2.f * eps_s;
+      int c_keep = 0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) c_keep += __popc(__ballot_sync(kFull, ev[e] >= keep));
+      if (c_keep <= CAP - 4) {
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (rank[e] < c_keep) {                // the kept entries are exactly the c_keep best-ranked
+            cvr[rank[e]] = ev[e];
+            cir[rank[e]] = ei[e] | ef[e];
+          }
+        }
+        new_n = c_keep;
+        new_thr = keep;
+      } else {
+        exact = true;                            // too many near-ties: settle them exactly
+      }
+    }
+    if (exact) {
+      const int rr = row0 + src;
+      const uint8_t* a_row = sA + (size_t)(rr >> 3) * (16 * DK) + (size_t)(rr & 7) * 16;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if (ef[e] && lane + 32 * e < ns) ev[e] = exact_score<DK>(a_row, Ib, ei[e]);
       }
       rank_entries<EPL>(ev, ei, rank);
-      bool exact = force || ns < k;
-      float new_thr = -INFINITY;
-      int new_n = ns;
-      if (!exact) {
-        float A = 0.f;                             // k-th largest value
+      __syncwarp();
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          const unsigned b = __ballot_sync(kFull, rank[e] == k - 1);
-          if (b) A = __shfl_sync(kFull, ev[e], __ffs(b) - 1);
+      for (int e = 0; e < EPL; ++e) {
+        if (lane + 32 * e < ns && rank[e] < k) {
+          cvr[rank[e]] = ev[e];
+          cir[rank[e]] = ei[e];
         }
-        const float keep = A - 2.f * eps_s;
-        int c_keep = 0;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) c_keep += __popc(__ballot_sync(kFull, ev[e] >= keep));
-        if (c_keep <= CAP - 4) {
-          __syncwarp();
-#pragma unroll
-          for (int e = 0; e < EPL; ++e) {
-            if (rank[e] < c_keep) {                // the kept entries are exactly the c_keep best-ranked
-              cvr[rank[e]] = ev[e];
-              cir[rank[e]] = ei[e] | ef[e];
-            }
-          }
-          new_n = c_keep;
-          new_thr = keep;
-        } else {
-          exact = true;                            // too many near-ties: settle them exactly
-        }
-      }
-      if (exact) {
-        const uint8_t* a_row = rc[src - lane].a_row;   // RowCtx of row (warp base + src)
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          if (ef[e] && lane + 32 * e < ns) ev[e] = exact_score<DK>(a_row, rc->Ib, ei[e]);
-        }
-        rank_entries<EPL>(ev, ei, rank);
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          if (lane + 32 * e < ns && rank[e] < k) {
-            cvr[rank[e]] = ev[e];
-            cir[rank[e]] = ei[e];
-          }
-        }
-        __syncwarp();
-        new_n = ns < k ? ns : k;
-        new_thr = (ns >= k) ? cvr[k - 1] - eps_s : -INFINITY;
       }
       __syncwarp();
-      if (lane == src) {
-        n = new_n;
-        thrf = fmaxf(thrf, new_thr);               // thresholds never move down
-        thr = __float2half_rd(thrf);
-      }
+      new_n = ns < k ? ns : k;
+      new_thr = (ns >= k) ? cvr[k - 1] - eps_s : -INFINITY;
+    }
+    __syncwarp();
+    if (lane == src) {
+      n = new_n;
+      thrf = fmaxf(thrf, new_thr);               // thresholds never move down
+    }
+    if (stats && lane == 0) {
+      atomicAdd(stats + 3, 1ull);
+      if (exact) atomicAdd(stats + 4, 1ull);
+      atomicAdd(stats + 5, (unsigned long long)(clock64() - c0));
     }
   }
   return pack_state(n, thrf);
@@ -404,7 +352,6 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
   __shared__ __align__(8) uint64_t bar_a;
   __shared__ uint32_t tmem_slot;
   __shared__ MaskCursor mc;
-  __shared__ RowCtx rctx[BM];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
                                              ~(uintptr_t)127);
@@ -511,10 +458,12 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
     // offered to the row iff its fp16-accumulated score is >= thr
     float thrf = (grow < B) ? -INFINITY : INFINITY;   // +inf: padded row, nothing survives
     if (dbg & 1) thrf = INFINITY;
+    // merge cursor over the row's training items (ascending CSR row of R): the next training item id
+    // lives in a register, the cursor itself in shared memory (only touched when it advances)
+    int mnext = 0x7fffffff;
     {
       const int32_t* c = mask_col;
       const int32_t* e = mask_col;
-      int mnext = 0x7fffffff;
       if (grow < B && mask_rowptr) {
         const int64_t uid = user_ids ? user_ids[grow] : grow;
         c = mask_col + mask_rowptr[uid];
@@ -523,7 +472,6 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
       }
       mc.cur[row] = c;
       mc.end[row] = e;
-      mc.next[row] = mnext;
     }
     // the row's norm (scaled units) from the resident A tile -> filter margin
     mbar_wait(&bar_a, 0);
@@ -542,103 +490,132 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
     }
     const float vmax = i_meta[2];                       // max scaled item-row norm
     const float eps = kEpsRel * sqrtf(un2) * vmax * 1.0001f + kEpsAbs;
-    RowCtx* rc = &rctx[row];
-    rc->a_row = a_row;
-    rc->Ib = Ih;
-    rc->cv = cv_warp + lane * CAP;
-    rc->ci = ci_warp + lane * CAP;
-    rc->eps = eps;
-    rc->m_items = m_items;
-    rc->k = k;
+    float* cv_row = cv_warp + lane * CAP;
+    int* ci_row = ci_warp + lane * CAP;
     __half thr = __float2half_rd(thrf);                 // -inf (or +inf for padded rows)
-    unsigned long long n_hits = 0, n_tiles_slow = 0;
+    unsigned long long n_hits = 0, n_tiles_slow = 0, c_slow = 0;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-
-    // filter + survivor path of one half tile: 64 scores of this row in x[0..31], first item id id0
-    auto consume = [&](uint32_t (&x)[32], int id0) {
-      // fast reject: four independent max chains over blocks of 8 registers (16 columns each)
-      uint32_t m0 = x[0], m1 = x[8], m2 = x[16], m3 = x[24];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        m0 = hmax2(m0, x[i]);
-        m1 = hmax2(m1, x[8 + i]);
-        m2 = hmax2(m2, x[16 + i]);
-        m3 = hmax2(m3, x[24 + i]);
+    uint32_t r[64];
+    for (int t = 0; t < n_item_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&bar_tfull[buf], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      if (dbg & 2) {   // bring-up: MMA side alone
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+        continue;
       }
-      const uint32_t mm = hmax2(hmax2(m0, m1), hmax2(m2, m3));
+      tmem_ld128h_issue(tq + (uint32_t)(buf * BN), r);
+      tmem_wait64(r);
+      // the whole quarter tile is in registers: hand the TMEM buffer back at once
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[buf]);
+      // fast reject: eight independent max chains over blocks of 8 registers (16 columns each),
+      // 63 HMNMX2 in all, one compare, one vote
+      uint32_t m[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        m[b] = r[8 * b];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m[b] = hmax2(m[b], r[8 * b + i]);
+      }
+      const uint32_t mm = hmax2(hmax2(hmax2(m[0], m[1]), hmax2(m[2], m[3])),
+                                hmax2(hmax2(m[4], m[5]), hmax2(m[6], m[7])));
       if (__any_sync(kFull, __hge(__hmax(lo_half(mm), hi_half(mm)), thr))) {
         // slow path: which 16-column blocks hold a hit in any lane
-        const unsigned bm = (__hge(__hmax(lo_half(m0), hi_half(m0)), thr) ? 1u : 0u) |
-                            (__hge(__hmax(lo_half(m1), hi_half(m1)), thr) ? 2u : 0u) |
-                            (__hge(__hmax(lo_half(m2), hi_half(m2)), thr) ? 4u : 0u) |
-                            (__hge(__hmax(lo_half(m3), hi_half(m3)), thr) ? 8u : 0u);
+        const long long c0 = stats ? clock64() : 0;
+        unsigned bm = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bm |= __hge(__hmax(lo_half(m[b]), hi_half(m[b])), thr) ? (1u << b) : 0u;
         unsigned blocks = __reduce_or_sync(kFull, bm);
         ++n_tiles_slow;
 #pragma unroll 1
         while (blocks) {
           const int bi = __ffs(blocks) - 1;
           blocks &= blocks - 1;
-          Pack8 p;
+          // warp-uniform pick of the block's eight packed registers (named scalars: an array written in
+          // a switch is placed in local memory by the compiler)
+          uint32_t p0, p1, p2, p3, p4, p5, p6, p7;
+#define SPEX_PICK(b)                                                                                   \
+  case b:                                                                                              \
+    p0 = r[8 * b]; p1 = r[8 * b + 1]; p2 = r[8 * b + 2]; p3 = r[8 * b + 3];                             \
+    p4 = r[8 * b + 4]; p5 = r[8 * b + 5]; p6 = r[8 * b + 6]; p7 = r[8 * b + 7];                         \
+    break;
+          switch (bi) {
+            SPEX_PICK(0) SPEX_PICK(1) SPEX_PICK(2) SPEX_PICK(3) SPEX_PICK(4) SPEX_PICK(5) SPEX_PICK(6)
+            default: SPEX_PICK(7)
+          }
+#undef SPEX_PICK
+          const uint32_t p[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+          // this lane's hits among the block's 16 columns, and the columns that hold a hit in any lane
+          const int id0 = t * BN + bi * 16;
+          unsigned mine = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)   // warp-uniform select of the block's eight packed registers
-            p.w[i] = bi == 0 ? x[i] : (bi == 1 ? x[8 + i] : (bi == 2 ? x[16 + i] : x[24 + i]));
-          const unsigned long long st = tf_group<DK, EPL>(p, thrf, id0 + bi * 16, n, lane, row, rc, &mc,
-                                                         cv_warp, ci_warp, false);
-          thrf = __uint_as_float((unsigned)(st & 0xffffffffull));
-          thr = __float2half_rd(thrf);
-          n = (int)(st >> 32);
+          for (int j = 0; j < 16; ++j) {
+            const __half a = (j & 1) ? hi_half(p[j >> 1]) : lo_half(p[j >> 1]);
+            mine |= __hge(a, thr) ? (1u << j) : 0u;
+          }
+          if (id0 + 16 > m_items) mine &= (id0 < m_items) ? ((1u << (m_items - id0)) - 1u) : 0u;   // tile padding
           ++n_hits;
+          // one lane-local append of a hit (filter score a, item id): merge cursor, two stores
+          auto offer = [&](__half a, int id) {
+            if (mnext < id) {                          // advance the merge cursor past id
+              const int32_t* c = mc.cur[row];
+              const int32_t* e = mc.end[row];
+              do {
+                ++c;
+                mnext = (c < e) ? __ldg(c) : 0x7fffffff;
+              } while (mnext < id);
+              mc.cur[row] = c;
+            }
+            if (mnext != id) {                         // == id: training item of this user, excluded
+              cv_row[n] = __half2float(a);
+              ci_row[n] = id | kApprox;
+              ++n;
+            }
+          };
+          auto compact = [&](unsigned need) {
+            const unsigned long long st = tf_compact<DK, EPL>(need, n, thrf, eps, k, lane, q * 32, sA, Ih,
+                                                             cv_warp, ci_warp, false, stats);
+            thrf = __uint_as_float((unsigned)(st & 0xffffffffull));
+            thr = __float2half_rd(thrf);
+            n = (int)(st >> 32);
+          };
+          if (!__any_sync(kFull, (mine & (mine - 1)) != 0)) {
+            // common case (all but the first few tiles): no lane has more than one hit in this block.
+            // Rows without room are compacted first, then every hit lane appends on its own.
+            const unsigned need = __ballot_sync(kFull, mine != 0 && n == CAP);
+            if (need) compact(need);
+            if (mine) {
+              const int j = __ffs(mine) - 1;
+              const uint32_t w = p[j >> 1];
+              const __half a = (j & 1) ? hi_half(w) : lo_half(w);
+              if (__hge(a, thr)) offer(a, id0 + j);    // thr may have risen in the compaction
+            }
+          } else {
+            // general case: visit, warp-uniformly, every column that holds a hit in some lane
+            unsigned cols = __reduce_or_sync(kFull, mine);
+#pragma unroll 1
+            while (cols) {
+              const int j = __ffs(cols) - 1;
+              cols &= cols - 1;
+              const unsigned need = __ballot_sync(kFull, ((mine >> j) & 1u) && n == CAP);
+              if (need) compact(need);
+              if ((mine >> j) & 1u) {
+                const uint32_t w = p[j >> 1];
+                const __half a = (j & 1) ? hi_half(w) : lo_half(w);
+                if (__hge(a, thr)) offer(a, id0 + j);
+              }
+            }
+          }
         }
-      }
-    };
-    // is the accumulator of tile t complete?  (polled once per tile, by the first half's request)
-    auto poll = [&](int t) {
-      mbar_wait(&bar_tfull[t & 1], (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
-    };
-    // both halves of tile t are in registers: hand the TMEM buffer back to the MMA warp at once
-    auto release = [&](uint32_t (&x)[32], uint32_t (&y)[32], int t) {
-      tmem_wait2(x, y);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[t & 1]);
-    };
-    // One tile with its scores in (X, Y) and Z free.  The first half of tile t+1 is requested into Z
-    // before X is reduced and its second half into X before Y is reduced, so the ~200-cycle TMEM
-    // reads are in flight behind the reductions; the next tile then lives in (Z, X) with Y free.
-    auto tile = [&](uint32_t (&X)[32], uint32_t (&Y)[32], uint32_t (&Z)[32], int t) {
-      release(X, Y, t);
-      const bool more = t + 1 < n_item_tiles;
-      const uint32_t nb = tq + (uint32_t)(((t + 1) & 1) * BN);
-      if (more) {
-        poll(t + 1);
-        tmem_ld64h_issue(nb, Z);
-      }
-      consume(X, t * BN);
-      if (more) tmem_ld64h_issue(nb + 64, X);
-      consume(Y, t * BN + 64);
-    };
-
-    if (dbg & 2) {   // bring-up: MMA side alone
-      for (int t = 0; t < n_item_tiles; ++t) {
-        poll(t);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[t & 1]);
-      }
-    } else if (n_item_tiles > 0) {
-      uint32_t b0[32], b1[32], b2[32];
-      poll(0);
-      tmem_ld64h_issue(tq, b0);
-      tmem_ld64h_issue(tq + 64, b1);
-      for (int t = 0; t < n_item_tiles; t += 3) {
-        tile(b0, b1, b2, t);
-        if (t + 1 < n_item_tiles) tile(b2, b0, b1, t + 1);
-        if (t + 2 < n_item_tiles) tile(b1, b2, b0, t + 2);
+        if (stats) c_slow += (unsigned long long)(clock64() - c0);
       }
     }
     // final compaction of every row (sorted best-first), then each thread writes its own row
-    n = (int)(tf_group<DK, EPL>(Pack8{}, thrf, 0, n, lane, row, rc, &mc, cv_warp, ci_warp, true) >> 32);
+    n = (int)(tf_compact<DK, EPL>(kFull, n, thrf, eps, k, lane, q * 32, sA, Ih, cv_warp, ci_warp, true, nullptr) >> 32);
     if (grow < B) {
       const float inv = u_meta[1] * i_meta[1];   // 2^-(s_u + s_i): exact
       for (int p = 0; p < k; ++p) {
@@ -647,9 +624,10 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
         out_val[grow * k + p] = ok ? cv_warp[lane * CAP + p] * inv : -INFINITY;
       }
     }
-    if (stats && lane == 0) {   // bring-up statistics: slow-path tiles and group calls per warp
-      atomicAdd(stats, n_tiles_slow);
-      atomicAdd(stats + 1, n_hits);
+    if (stats && lane == 0) {   // bring-up statistics, summed over epilogue warps: slow-path tiles, block
+      atomicAdd(stats, n_tiles_slow);      // calls, cycles in the slow path; tf_compact adds [3] compactions,
+      atomicAdd(stats + 1, n_hits);        // [4] exact compactions, [5] cycles in compactions
+      atomicAdd(stats + 2, c_slow);
     }
   }
   tc_fence_before();
@@ -780,9 +758,11 @@ static int launch_k(const void* Uh, const void* Ih, int64_t B, int64_t B_pad, in
                     const int64_t* mask_rowptr, const int32_t* mask_col, int32_t k, int32_t* out_idx,
                     float* out_val, cudaStream_t st) {
   // candidate buffer capacity CAP = 32*EPL must hold the k kept entries + room to append
-  if (k <= 24)
+  int epl_min = 1;
+  if (const char* e = getenv("SPEX_TF_EPL")) epl_min = atoi(e);   // bring-up experiment
+  if (k <= 24 && epl_min <= 1)
     return launch<DK, 1>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
-  if (k <= 56)
+  if (k <= 56 && epl_min <= 2)
     return launch<DK, 2>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
   return launch<DK, 3>(Uh, Ih, B, B_pad, m_items, m_pad, u_meta, i_meta, user_ids, mask_rowptr, mask_col, k, out_idx, out_val, st);
 }
