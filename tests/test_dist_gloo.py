@@ -52,13 +52,10 @@ def _worker(rank, world, port, K, q):
             nxt = tables[j + 1] if j + 1 < len(tables) else mine * 3.0   # the last announcement is never used
             outs.append(prop.propagate(t, next_E0_local=nxt))
         stale = prop.propagate(mine)   # announced table was mine * 3: must be ignored
-        ring_ok = (torch.equal(outs[0], out) and torch.equal(outs[3], out) and torch.equal(stale, out)
-                   and torch.allclose(outs[1], out * 2.0 - 0.5 * 0 + (outs[1] - out * 2.0), atol=0))
-        # linearity check of the shifted tables against a direct (unannounced) call
         direct1 = prop.propagate(tables[1].clone())
-        ring_ok = ring_ok and torch.equal(outs[1], direct1)
         direct2 = prop.propagate(tables[2].clone())
-        ring_ok = ring_ok and torch.equal(outs[2], direct2)
+        ring_ok = (torch.equal(outs[0], out) and torch.equal(outs[3], out) and torch.equal(stale, out)
+                   and torch.equal(outs[1], direct1) and torch.equal(outs[2], direct2))
         ru, ri = O.computer(E[: nu + 1], E[nu + 1:], oracle_graph(u, i, nu + 1, m), K)
         want = torch.cat([ru, ri])[bounds[rank]: bounds[rank + 1]]
         err = float((out - want).abs().max())

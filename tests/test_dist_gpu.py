@@ -64,9 +64,30 @@ def _worker(rank, world, port, q):
             prop.timing = []
             c = prop.propagate(E[r0:r1].clone())
             phases = [n for n, _ in prop.phase_ms()]
+            # a sweep over different tables, each announced one call ahead (published to the peers by the
+            # background kernel during the previous call's last layer), then an unannounced call
+            ok_ring = True
+            if prop.can_prefetch():
+                tabs = [E[r0:r1].clone(), (E[r0:r1] * 2.0 - 0.5).clone(), (E[r0:r1] * -1.0).clone(), E[r0:r1].clone()]
+                outs = [prop.propagate(t, next_E0_local=tabs[j + 1] if j + 1 < len(tabs) else tabs[1])
+                        for j, t in enumerate(tabs)]
+                stale = prop.propagate(tabs[0])           # the announced table was tabs[1]: must be ignored
+                d1 = prop.propagate(tabs[1].clone())
+                d2 = prop.propagate(tabs[2].clone())
+                ok_ring = (torch.equal(outs[0], a) and torch.equal(outs[3], a) and torch.equal(stale, a)
+                           and torch.equal(outs[1], d1) and torch.equal(outs[2], d2))
             prop.close()
-            res[f"{mode}/{e0}"] = (bool(torch.equal(a, want[r0:r1])), bool(torch.equal(a, b) and torch.equal(a, c)),
-                                   phases)
+            res[f"{mode}/{e0}"] = (bool(torch.equal(a, want[r0:r1])),
+                                   bool(torch.equal(a, b) and torch.equal(a, c) and ok_ring), phases)
+        # a width that takes the generic-D kernel (its epilogue ignored the multicast table)
+        D2 = 48
+        E2 = (torch.randn(N, D2, generator=torch.Generator().manual_seed(1)) * 0.1).to(dev)
+        want2 = ops.propagate_mean(E2, full, K)
+        for mode in [m for m, e in modes if m == e and m != "nccl"]:
+            prop = PartitionedPropagator(lg, bounds, D2, K, mode=mode, device=dev)
+            a2 = prop.propagate(E2[r0:r1].clone())
+            prop.close()
+            res[f"{mode}/D48"] = (bool(torch.equal(a2, want2[r0:r1])), True, ["layer3", "e0_exchange"])
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
