@@ -50,7 +50,14 @@ def parse():
                     help="auto = mcast (NVLS multicast stores) when the box supports it, else push")
     ap.add_argument("--e0-exchange", default=os.environ.get("SPEX_E0_EXCHANGE"), choices=["nccl", "push", "copy", "mcast"],
                     help="how E^(0) is all-gathered in push / mcast mode")
-    ap.add_argument("--eval-users", type=int, default=148 * 2 * 128)
+    ap.add_argument("--eval-users", type=int, default=0,
+                    help="users ranked by the evaluation sweep, whole job (0 = all users of the workload)")
+    ap.add_argument("--eval-scorer", default="f16", choices=["f16", "bf16"],
+                    help="f16: fp16-accumulator filter + exact re-score (r02); bf16: round 1's fp32-accumulator kernel")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=256, help="samples per train step (main_rec.py:20: 256)")
+    ap.add_argument("--loss-bench-batch", type=int, default=1 << 20,
+                    help="batch on which the loss / scatter kernels are timed alone for their rooflines")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -232,6 +239,138 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- training step -------------------------------------------------------------------------------------
+def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, peak_kind, dev):
+    """One optimiser step of the reference loop (LightGCN_SPEX/code/main_rec.py:30-37) on the bench graph:
+    computer() forward, gather + dot + BCEWithLogits, backward (deterministic scatter, K A^T SpMMs), dense
+    Adam over the fused table - through the public operators, persistent workspaces on.  Per-phase CUDA
+    events, and the loss / scatter / Adam / dropout-value kernels timed alone on a large batch for their
+    HBM rooflines (algorithmic bytes per sample or element as in DESIGN.md §4)."""
+    from spex_b200.dataloader import sample_negatives_device
+
+    ops.enable_persistent_workspaces(True)
+    W = table.clone().requires_grad_(True)
+    mom, var = torch.zeros_like(W), torch.zeros_like(W)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    B = args.train_batch
+    nu = nur - 1
+
+    def batch(n):
+        # reference sampling (dataloader.py:250-265): one positive + 5 rejection-sampled negatives
+        u = torch.randint(0, nu, (n // 6 + 1,), device=dev, generator=gen)
+        e = g.rowptr[u] + (torch.rand(u.numel(), device=dev, generator=gen) * (g.rowptr[u + 1] - g.rowptr[u])).long()
+        pos = (g.col[e] & 0x7FFFFFFF).long() - nur
+        neg = sample_negatives_device(g.rowptr, g.col, nur, m, u, 5, seed=int(n) + 1)
+        users = torch.cat([u, u.repeat_interleave(5)])[:n].contiguous()
+        items = torch.cat([pos, neg.reshape(-1)])[:n].contiguous()
+        labels = torch.cat([torch.ones_like(u), torch.zeros(u.numel() * 5, dtype=u.dtype, device=dev)])[:n]
+        return users, items, labels.float().contiguous()
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    step_no = [0]
+
+    def train_step(users, items, labels, marks=None):
+        W.grad = None
+        t0 = ev() if marks is not None else None
+        out = ops.propagate_mean(W, g, K_LAYERS)
+        t1 = ev() if marks is not None else None
+        loss = ops.bce_loss(out, nur, users, items, labels)
+        t2 = ev() if marks is not None else None
+        loss.backward()
+        t3 = ev() if marks is not None else None
+        step_no[0] += 1
+        ops.adam_step(W.data, W.grad, mom, var, 1e-3, 0.9, 0.999, 1e-8, step_no[0])
+        t4 = ev() if marks is not None else None
+        if marks is not None:
+            marks.append((t0, t1, t2, t3, t4))
+        return loss
+
+    users, items, labels = batch(B)
+    for _ in range(2):
+        train_step(users, items, labels)
+    torch.cuda.synchronize()
+    n_steps = 4
+    e0 = ev()
+    for _ in range(n_steps):
+        loss = train_step(users, items, labels)
+    e1 = ev()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / n_steps
+    marks = []
+    train_step(users, items, labels, marks)
+    torch.cuda.synchronize()
+    t0, t1, t2, t3, t4 = marks[0]
+    phases = {"forward_propagate_ms": t0.elapsed_time(t1), "bce_forward_ms": t1.elapsed_time(t2),
+              "backward_scatter_plus_propagate_ms": t2.elapsed_time(t3), "adam_ms": t3.elapsed_time(t4)}
+    loss_val = float(loss.item())
+
+    # kernels alone, large batch, with their algorithmic bytes
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a = ev()
+        for _ in range(reps):
+            fn()
+        b = ev()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    Bl = args.loss_bench_batch
+    ul, il, ll = batch(Bl)
+    out = ops.propagate_mean(W.detach(), g, K_LAYERS)
+    U, I = out[:nur], out[nur:]
+    row = 4 * D
+    gam = torch.empty(Bl, device=dev)
+    dgam = torch.empty(Bl, device=dev)
+    lo = torch.empty(1, device=dev)
+    kern = {}
+    ms = timed(lambda: _capi.call("spex_bce_fwd_f32", _capi.ptr(U), _capi.ptr(I), D, _capi.ptr(ul), _capi.ptr(il),
+                                  _capi.ptr(ll), Bl, _capi.ptr(gam), _capi.ptr(lo), _capi.ptr(dgam), _capi.stream_ptr()))
+    kern["bce_fwd_kernel"] = (ms, Bl * (2 * row + 16 + 4 + 8))
+    gbuf = torch.zeros_like(out)
+    work, wb = ops._scatter_workspace(Bl, dev)
+    ms = timed(lambda: _capi.call("spex_bce_bwd_ws_f32", _capi.ptr(U), _capi.ptr(I), D, _capi.ptr(ul), _capi.ptr(il),
+                                  _capi.ptr(dgam), None, Bl, _capi.ptr(gbuf[:nur]), _capi.ptr(gbuf[nur:]),
+                                  _capi.ptr(work), wb, _capi.stream_ptr()))
+    # two lists: each entry reads one row and its run writes one row; + sort traffic 2 x 4 passes x 16 B
+    kern["scatter_sorted (keys + radix sort + scatter_sorted_kernel, x2 lists)"] = (ms, 2 * Bl * (2 * row + 16 + 128))
+    pu, pp, pn = ul, il, torch.randint(0, m, (Bl,), device=dev, generator=gen)
+    out2, dsc, wk = torch.empty(2, device=dev), torch.empty(Bl, device=dev), torch.empty(2 * Bl, device=dev)
+    Wd = W.detach()
+    ms = timed(lambda: _capi.call("spex_bpr_fwd_f32", _capi.ptr(U), _capi.ptr(I), _capi.ptr(Wd[:nur]), _capi.ptr(Wd[nur:]),
+                                  D, _capi.ptr(pu), _capi.ptr(pp), _capi.ptr(pn), Bl, _capi.ptr(out2), _capi.ptr(dsc),
+                                  _capi.ptr(wk), _capi.stream_ptr()))
+    kern["bpr_fwd_kernel"] = (ms, Bl * (6 * row + 24 + 12))
+    del gbuf
+    gg = torch.empty_like(Wd)
+    gg.normal_(generator=gen)
+    ms = timed(lambda: ops.adam_step(Wd, gg, mom, var, 1e-3, 0.9, 0.999, 1e-8, 3))
+    kern["adam_kernel"] = (ms, W.numel() * 28)
+    del gg
+    keep = torch.ones(g.nnz, device=dev)
+    vout = torch.empty_like(g.val)
+    ms = timed(lambda: _capi.call("spex_gather_f32", _capi.ptr(g.val), None, _capi.ptr(keep), 0.6, _capi.ptr(vout), g.nnz,
+                                  _capi.stream_ptr()), reps=3)
+    kern["gather_scale_kernel (edge-dropout values, model.py:46-55)"] = (ms, g.nnz * 12)
+    del keep, vout
+    roofs = {k: {"ms": round(v[0], 4), "algorithmic_bytes": v[1], "achieved": v[1] / v[0] / 1e6, "unit": "GB/s",
+                 "peak": hbm_peak, "frac": v[1] / v[0] / 1e6 / hbm_peak, "peak_kind": peak_kind, "bound": "hbm"}
+             for k, v in kern.items()}
+    ops.enable_persistent_workspaces(False)
+    return {"metric": "lightgcn_train_step_ms", "value": ms_step, "unit": "ms", "higher_is_better": False,
+            "steps_per_s": 1e3 / ms_step, "batch": B, "loss": loss_val, "phases_ms": {k: round(v, 3) for k, v in phases.items()},
+            "config": {"workload": f"main_rec.py:30-37 step on the bench graph: forward(K={K_LAYERS}) + BCE (1 positive + 5 "
+                                   f"negatives per user, device sampler) + backward + dense Adam over {N} x {D}",
+                       "edges_per_step": 2 * K_LAYERS * g.nnz},
+            "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * g.nnz / (ms_step * 1e-3) / 1e9,
+            "kernel_rooflines": roofs, "loss_bench_batch": Bl}
 
 
 # ---- our arm -----------------------------------------------------------------------------------------
@@ -549,7 +688,15 @@ def run_ours(args):
     if clocks:
         clocks.mark(False)
 
-    # ---- secondary: full-ranking top-20 (users sharded by rank, no communication) ----
+    # ---- e2e buffers are no longer needed: make room for the evaluation and training legs ----
+    if not args.no_e2e:
+        del h_in, h_out, d_in, d_out
+    torch.cuda.empty_cache()
+
+    # ---- secondary: full-ranking top-20 over ALL users (BASELINE.json configs[4]) ----
+    # users sharded by rank (no communication), the propagated item table replicated; one step = the
+    # whole sweep: per block of users, pack the user rows (fp16, scaled) + one launch of the tcgen05
+    # scorer (filter + mask + top-k); results stay on the device ([users, 20] ids and scores).
     evalj = None
     if not args.no_eval:
         if world == 1:
@@ -559,39 +706,95 @@ def run_ours(args):
             full = torch.empty(N, D, dtype=torch.float32, device=dev)
             prop._all_gather_rows(full, res)
             U_all, I_all = full[:nur], full[nur:]
-        n_eval = min(args.eval_users, nu)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(7 + rank)
-        users = torch.randint(0, nu, (n_eval,), device=dev, generator=gen)
-        Ib, m_pad = ops.pack_bf16(I_all, None, ops.TC_ITEM_MULTIPLE)
+        n_total = min(args.eval_users, nu) if args.eval_users > 0 else nu
+        u_lo, u_hi = (n_total * rank) // world, (n_total * (rank + 1)) // world
+        n_eval = u_hi - u_lo
+        users = torch.arange(u_lo, u_hi, device=dev)
+        blk = 148 * 2 * 128 * 4
         idx = torch.empty(n_eval, TOPK, dtype=torch.int32, device=dev)
         val = torch.empty(n_eval, TOPK, dtype=torch.float32, device=dev)
+        if args.eval_scorer == "f16":
+            Ih, m_pad, imeta = ops.pack_f16(I_all, None, ops.TC_ITEM_MULTIPLE)
+        else:
+            Ib, m_pad = ops.pack_bf16(I_all, None, ops.TC_ITEM_MULTIPLE)
 
-        def eval_step():
-            Ub, b_pad = ops.pack_bf16(U_all, users, ops.TC_USER_MULTIPLE)
-            ops.score_topk_bf16(Ub, n_eval, b_pad, Ib, m, m_pad, TOPK, users, mask_rp, mask_col, idx, val)
+        def eval_sweep(limit=None):
+            hi = n_eval if limit is None else min(limit, n_eval)
+            for a in range(0, hi, blk):
+                ub = users[a: min(a + blk, hi)]
+                if args.eval_scorer == "f16":
+                    Uh, b_pad, umeta = ops.pack_f16(U_all, ub, ops.TC_USER_MULTIPLE)
+                    ops.score_topk_f16(Uh, umeta, ub.numel(), b_pad, Ih, imeta, m, m_pad, D, TOPK, ub, mask_rp,
+                                       mask_col, idx[a: a + ub.numel()], val[a: a + ub.numel()])
+                else:
+                    Ub, b_pad = ops.pack_bf16(U_all, ub, ops.TC_USER_MULTIPLE)
+                    ops.score_topk_bf16(Ub, ub.numel(), b_pad, Ib, m, m_pad, TOPK, ub, mask_rp, mask_col,
+                                        idx[a: a + ub.numel()], val[a: a + ub.numel()])
 
-        eval_step()
+        eval_sweep(blk)   # warm-up on one block
         barrier()
-        n_ev = 3
         ev0.record()
-        for _ in range(n_ev):
-            eval_step()
+        eval_sweep()
         ev1.record()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_ev = float(t.item()) / n_ev
+        ms_ev = float(t.item())
         flops = 2.0 * n_eval * m * D
         tf = flops / (ms_ev * 1e-3) / 1e12
-        evalj = {"metric": "fullrank_top20_users_per_s", "value": n_eval * world / (ms_ev * 1e-3),
-                 "unit": "users/s", "users_per_step_per_gpu": n_eval, "m_items": m, "ms_per_step": ms_ev,
-                 "roofline": {"bound": "tensor", "kernel": "score_topk_tc_kernel", "achieved": tf,
-                              "peak": tc_burst, "unit": "TFLOP/s", "frac": tf / tc_burst,
-                              "peak_kind": peak_kind,
-                              "traffic": 861.8e6 if (world == 1 and args.scale == 1.0 and
-                                                     n_eval == 148 * 2 * 128) else None}}
+        # untimed sanity on the last block: sorted best-first, in range, and equal to the exact fp32 scorer
+        # on 256 of its users (same top-20 scores to 2e-3 relative: fp16 / bf16 operand rounding)
+        chk = torch.arange(max(n_eval - 256, 0), n_eval, device=dev)
+        i32, v32 = ops.score_topk_f32(U_all, I_all, users[chk], TOPK, mask_rp, mask_col)
+        sc = float(v32.abs().max())
+        eval_ok = bool((val[chk][:, :-1] >= val[chk][:, 1:]).all()) and bool((idx[chk] >= 0).all()) and \
+            bool((idx[chk] < m).all()) and float((val[chk] - v32).abs().max()) <= (2e-3 if args.eval_scorer == "f16" else 1e-2) * sc
+        agree = float((idx[chk] == i32).float().mean())
+        # CPU leg of metric 2 (rank 0, N = 1): torch.matmul + masked_fill + topk on the same tables
+        cpu_eval = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n_cpu = 128
+            Uc, Ic = U_all[:n_cpu].cpu(), I_all.cpu()
+            rp_c, col_c = mask_rp[: n_cpu + 1].cpu(), mask_col[: int(mask_rp[n_cpu].item())].cpu().long()
+            rows_c = torch.repeat_interleave(torch.arange(n_cpu), rp_c[1:] - rp_c[:-1])
+
+            def cpu_rank():
+                sco = torch.matmul(Uc, Ic.t())
+                sco[rows_c, col_c] = float("-inf")
+                return torch.topk(sco, TOPK, dim=1)
+
+            cpu_rank()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                cv, ci = cpu_rank()
+            dtc = (time.perf_counter() - t0) / 2
+            same = float((ci.to(dev).int() == ops.score_topk_f32(U_all, I_all, torch.arange(n_cpu, device=dev), TOPK,
+                                                                 mask_rp, mask_col)[0]).float().mean())
+            cpu_eval = {"value": n_cpu / dtc, "unit": "users/s", "cores": cores, "kind": "port",
+                        "sample": f"torch.matmul + masked_fill + topk(20), {n_cpu} users x {m} items, D={D}, fp32, "
+                                  f"2 timed runs, {dtc * 1e3:.0f} ms each; top-20 ids equal to the fp32 GPU scorer: {same:.4f}"}
+            del Uc, Ic
+        evalj = {"metric": "fullrank_top20_users_per_s", "value": n_total / (ms_ev * 1e-3),
+                 "unit": "users/s", "users_ranked": n_total, "users_per_gpu": n_eval, "m_items": m, "ms_per_sweep": ms_ev,
+                 "scorer": args.eval_scorer, "check": {"ok": eval_ok, "top20_ids_equal_to_fp32_scorer": agree},
+                 "config": {"workload": f"full-ranking top-20 sweep, {n_total} users x {m} items, D={D}, user-sharded x{world} "
+                                        "(BASELINE.json configs[4])"},
+                 "roofline": {"bound": "tensor", "kernel": "score_topk_f16_kernel<64,1>" if args.eval_scorer == "f16"
+                              else "score_topk_tc_kernel<1>", "achieved": tf, "peak": tc_burst, "unit": "TFLOP/s",
+                              "frac": tf / tc_burst, "peak_kind": peak_kind,
+                              "frac_of_sustained_peak": tf / tc_sust, "traffic": None},
+                 "cpu_baseline": cpu_eval}
+        del idx, val, users
+        if world > 1:
+            del full
+
+    # ---- training step (main_rec.py:30-37): forward + BCE + backward + dense Adam, N = 1 ----
+    trainj = None
+    if world == 1 and not args.no_train:
+        trainj = bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, peak_kind, dev)
 
     launches_total = _capi.launch_count() - launches0
     ck = clocks.stop() if clocks else None
@@ -624,7 +827,7 @@ def run_ours(args):
                        "e0_prefetch_during_last_layer": bool(world > 1 and prefetch),
                        "numa_cpus_rank0": numa_cpus,
                        "phase_ms_max_over_ranks": phase_log},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "train_step": trainj, "parity": parity,
             "output_table_hash64": out_hash,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
         }

@@ -155,6 +155,20 @@ int spex_bce_fwd_f32(const float* U, const float* I, int32_t D,
 int spex_bce_bwd_f32(const float* U, const float* I, int32_t D,
                      const int64_t* users, const int64_t* items, const float* dgamma,
                      const float* grad_loss, int64_t B, float* gU, float* gI, void* stream);
+/* The same with a workspace: from a few thousand samples on, the duplicate scan (O(B^2/32)) is
+ * replaced by a stable radix sort of (row, position) pairs + one warp per run - same summation
+ * order (ascending batch position), bit-identical gradients.  work: device, 16-byte aligned,
+ * >= spex_scatter_workspace_bytes(max list length) bytes (list length: B for BCE, 2B for BPR);
+ * NULL selects the scan (<= 2^18 entries). */
+int64_t spex_scatter_workspace_bytes(int64_t total_entries);
+int spex_bce_bwd_ws_f32(const float* U, const float* I, int32_t D,
+                        const int64_t* users, const int64_t* items, const float* dgamma,
+                        const float* grad_loss, int64_t B, float* gU, float* gI,
+                        void* work, int64_t work_bytes, void* stream);
+/* table[rows[i], :] = 0 for i < n: re-zeroes the rows a backward scatter touched, so that the dense
+ * gradient buffer of the propagated table (N x D, 3.84 GB on the 1B-edge graph) is zero-filled
+ * once, not every step (replaces the zeros_like of autograd's index backward, main_rec.py:35). */
+int spex_clear_rows_f32(float* table, const int64_t* rows, int64_t n, int32_t D, void* stream);
 
 /*
  * BPR step (north_star addition; semantics of upstream LightGCN bpr_loss):
@@ -177,6 +191,11 @@ int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const floa
                      const int64_t* users, const int64_t* pos, const int64_t* neg,
                      const float* dscore, const float* grad2, int64_t B,
                      float* gU, float* gI, float* gU0, float* gI0, void* stream);
+int spex_bpr_bwd_ws_f32(const float* U, const float* I, const float* U0, const float* I0, int32_t D,
+                        const int64_t* users, const int64_t* pos, const int64_t* neg,
+                        const float* dscore, const float* grad2, int64_t B,
+                        float* gU, float* gI, float* gU0, float* gI0,
+                        void* work, int64_t work_bytes, void* stream);
 
 /*
  * Dense Adam over one table (torch.optim.Adam semantics, main_rec.py:23,37; K7):
@@ -185,6 +204,24 @@ int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const floa
  */
 int spex_adam_f32(float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/*
+ * Device-side samplers (replace the host loop of LightTrainData.ng_sample,
+ * LightGCN_SPEX/code/utility1/dataloader.py:250-265, and give bpr_loss its triples).
+ * (rowptr, col) = the adjacency CSR: the row of user u lists its training items as
+ * item_col_offset + item (ascending; bit 31 may carry the hot flag).  Counter-based randomness:
+ * the same seed gives the same samples on every launch.
+ *   spex_sample_negatives: out int64 [n, n_neg], out[s, q] uniform over the items user users[s]
+ *                          has NOT interacted with (-1 only if it interacted with every item);
+ *   spex_sample_bpr:       users/pos/neg int64 [n]: user uniform over users with >= 1 interaction,
+ *                          pos uniform over its items, neg as above.
+ */
+int spex_sample_negatives(const int64_t* rowptr, const int32_t* col, int32_t item_col_offset,
+                          int32_t m_items, const int64_t* users, int64_t n, int32_t n_neg,
+                          uint64_t seed, int64_t* out, void* stream);
+int spex_sample_bpr(const int64_t* rowptr, const int32_t* col, int32_t item_col_offset, int32_t m_items,
+                    int64_t n_users, int64_t n, uint64_t seed, int64_t* users, int64_t* pos,
+                    int64_t* neg, void* stream);
 
 /*
  * Expert gating epilogue (configs[1], model_expert_s.py:154-161):

@@ -53,9 +53,15 @@ SIGNATURES = {
     "spex_gather_f32": (C.c_int, [_p, _p, _p, _f, _p, _i64, _p]),
     "spex_bce_fwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "spex_bce_bwd_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i64, _p, _p, _p]),
+    "spex_scatter_workspace_bytes": (_i64, [_i64]),
+    "spex_bce_bwd_ws_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
+    "spex_clear_rows_f32": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "spex_bpr_bwd_ws_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
     "spex_bpr_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "spex_bpr_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "spex_adam_f32": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i32, _p]),
+    "spex_sample_negatives": (C.c_int, [_p, _p, _i32, _i32, _p, _i64, _i32, C.c_uint64, _p, _p]),
+    "spex_sample_bpr": (C.c_int, [_p, _p, _i32, _i32, _i64, _i64, C.c_uint64, _p, _p, _p, _p]),
     "spex_expert_gate_f32": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p]),
     "spex_expert_gate_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "spex_score_topk_f32": (C.c_int, [_p, _p, _i32, _p, _i64, _i64, _p, _p, _i32, _p, _p, _p]),
@@ -82,7 +88,7 @@ SIGNATURES = {
     ),
 }
 
-_NO_STATUS = {"spex_abi_version", "spex_error_string", "spex_launch_count"}
+_NO_STATUS = {"spex_abi_version", "spex_error_string", "spex_launch_count", "spex_scatter_workspace_bytes"}
 
 
 class SpexLibraryMissing(ImportError):

@@ -15,6 +15,7 @@
 // are bit-reproducible.
 #include "common.cuh"
 #include <math.h>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace spex {
 
@@ -147,10 +148,98 @@ scatter_rows_kernel(ScatterList L, const float* __restrict__ src, float* __restr
   }
 }
 
-static int launch_scatter(const ScatterList& L, const float* src, float* out, int D, cudaStream_t st) {
+// ---- sorted form (large batches) -------------------------------------------------------------------
+// The scan above costs O(total^2 / 32); from a few thousand entries on the list is instead SORTED by
+// destination row (stable LSB radix sort of (row, t) pairs: entries of a row stay in ascending t) and
+// the warp that owns the FIRST entry of a row's run sums the run in order.  Same summation order as
+// the scan (ascending t), so both forms give bit-identical gradients.
+__global__ void __launch_bounds__(256)
+scatter_keys_kernel(ScatterList L, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t total = (int64_t)L.nseg * L.B;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < total; t += stride) {
+    const int sg = (int)(t / L.B);
+    keys[t] = (uint32_t)L.idx[sg][t - (int64_t)sg * L.B];
+    vals[t] = (uint32_t)t;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+scatter_sorted_kernel(ScatterList L, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                      const float* __restrict__ src, float* __restrict__ out, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)L.nseg * L.B;
+  const int64_t p = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (p >= total) return;
+  const uint32_t my = keys[p];
+  if (p > 0 && keys[p - 1] == my) return;   // not the head of its row's run
+  const float gs = (L.gscalar ? L.gscalar[0] : 1.f) * L.cconst;
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = f4_zero();
+  for (int64_t e = p; e < total && keys[e] == my; ++e) {
+    const int64_t t2 = vals[e];
+    const int sg = (int)(t2 / L.B);
+    const int64_t b2 = t2 - (int64_t)sg * L.B;
+    const float w = L.sign[sg] * (L.coef ? L.coef[b2] : 1.f) * gs;
+    float4 r[NV];
+    load_row<NV>(src, L.src_idx[sg][b2], D, lane, r);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) f4_fma(acc[v], w, r[v]);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int d = (lane + 32 * v) * 4;
+    if (d < D) *reinterpret_cast<float4*>(out + (int64_t)my * D + d) = acc[v];
+  }
+}
+
+constexpr int64_t kScanLimit = 2048;       // above: sorted form (needs a workspace)
+constexpr int64_t kScatterMax = 1ll << 31;  // entries (positions travel as uint32)
+
+static size_t scatter_cub_bytes(int64_t total) {
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)total);
+  return tmp;
+}
+static int64_t scatter_ws_bytes(int64_t total) {
+  if (total <= kScanLimit) return 0;
+  const int64_t arr = ((total * 4 + 255) / 256) * 256;
+  return 4 * arr + (int64_t)((scatter_cub_bytes(total) + 255) / 256 * 256);
+}
+
+static int launch_scatter(const ScatterList& L, const float* src, float* out, int D, void* work,
+                          int64_t work_bytes, cudaStream_t st) {
   const int64_t total = (int64_t)L.nseg * L.B;
   if (total == 0) return 0;
-  if (total > (1 << 18)) return SPEX_E_TOOBIG;  // O(total^2/32) duplicate scan; see DESIGN.md
+  if (total > kScanLimit && work) {
+    SPEX_RETURN_IF(total >= kScatterMax, SPEX_E_TOOBIG);
+    SPEX_RETURN_IF(work_bytes < scatter_ws_bytes(total) || !aligned16(work), SPEX_E_WORKSPACE);
+    const int64_t arr = ((total * 4 + 255) / 256) * 256;
+    uint8_t* w8 = (uint8_t*)work;
+    uint32_t* k_in = (uint32_t*)w8;
+    uint32_t* k_out = (uint32_t*)(w8 + arr);
+    uint32_t* v_in = (uint32_t*)(w8 + 2 * arr);
+    uint32_t* v_out = (uint32_t*)(w8 + 3 * arr);
+    void* tmp = w8 + 4 * arr;
+    size_t tmp_bytes = scatter_cub_bytes(total);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scatter_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(L, k_in, v_in);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)total, 0, 32, st);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)((total + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (D <= 128)
+      scatter_sorted_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(L, k_out, v_out, src, out, D);
+    else
+      scatter_sorted_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(L, k_out, v_out, src, out, D);
+    count_launch(2);
+    return check_last();
+  }
+  if (total > (1 << 18)) return SPEX_E_WORKSPACE;  // O(total^2/32) duplicate scan: pass a workspace
   const unsigned grid = (unsigned)((total + kWarpsPerCta - 1) / kWarpsPerCta);
   if (D <= 128)
     scatter_rows_kernel<1><<<grid, kWarpsPerCta * 32, 0, st>>>(L, src, out, D);
@@ -158,6 +247,17 @@ static int launch_scatter(const ScatterList& L, const float* src, float* out, in
     scatter_rows_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(L, src, out, D);
   count_launch();
   return check_last();
+}
+
+// out[rows[i], :] = 0  (thread per float4; duplicate rows are harmless)
+__global__ void __launch_bounds__(256)
+clear_rows_kernel(float* __restrict__ table, const int64_t* __restrict__ rows, int64_t n, int D4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n * D4; i += stride) {
+    const int64_t r = rows[i / D4];
+    reinterpret_cast<float4*>(table)[r * D4 + (i % D4)] = f4_zero();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -442,9 +542,26 @@ extern "C" int spex_bce_fwd_f32(const float* U, const float* I, int32_t D, const
   return check_last();
 }
 
-extern "C" int spex_bce_bwd_f32(const float* U, const float* I, int32_t D, const int64_t* users,
-                                const int64_t* items, const float* dgamma, const float* grad_loss,
-                                int64_t B, float* gU, float* gI, void* stream) {
+extern "C" int64_t spex_scatter_workspace_bytes(int64_t total_entries) {
+  return total_entries < 0 ? 0 : scatter_ws_bytes(total_entries);
+}
+
+extern "C" int spex_clear_rows_f32(float* table, const int64_t* rows, int64_t n, int32_t D, void* stream) {
+  SPEX_RETURN_IF(!table || (n > 0 && !rows) || n < 0, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(table), SPEX_E_ALIGN);
+  if (n == 0) return 0;
+  int64_t blocks = (n * (D / 4) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  clear_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, rows, n, D / 4);
+  count_launch();
+  return check_last();
+}
+
+extern "C" int spex_bce_bwd_ws_f32(const float* U, const float* I, int32_t D, const int64_t* users,
+                                   const int64_t* items, const float* dgamma, const float* grad_loss,
+                                   int64_t B, float* gU, float* gI, void* work, int64_t work_bytes,
+                                   void* stream) {
   SPEX_RETURN_IF(!U || !I || !users || !items || !dgamma || !gU || !gI || B < 0, SPEX_E_BADARG);
   SPEX_CHECK_TABLE(D);
   SPEX_RETURN_IF(!aligned16(U) || !aligned16(I) || !aligned16(gU) || !aligned16(gI), SPEX_E_ALIGN);
@@ -459,12 +576,18 @@ extern "C" int spex_bce_bwd_f32(const float* U, const float* I, int32_t D, const
   // gU[users] += dgamma * I[items]
   L.idx[0] = users;
   L.src_idx[0] = items;
-  int rc = launch_scatter(L, I, gU, D, st);
+  int rc = launch_scatter(L, I, gU, D, work, work_bytes, st);
   if (rc) return rc;
   // gI[items] += dgamma * U[users]
   L.idx[0] = items;
   L.src_idx[0] = users;
-  return launch_scatter(L, U, gI, D, st);
+  return launch_scatter(L, U, gI, D, work, work_bytes, st);
+}
+
+extern "C" int spex_bce_bwd_f32(const float* U, const float* I, int32_t D, const int64_t* users,
+                                const int64_t* items, const float* dgamma, const float* grad_loss,
+                                int64_t B, float* gU, float* gI, void* stream) {
+  return spex_bce_bwd_ws_f32(U, I, D, users, items, dgamma, grad_loss, B, gU, gI, nullptr, 0, stream);
 }
 
 extern "C" int spex_bpr_fwd_f32(const float* U, const float* I, const float* U0, const float* I0,
@@ -487,11 +610,11 @@ extern "C" int spex_bpr_fwd_f32(const float* U, const float* I, const float* U0,
   return check_last();
 }
 
-extern "C" int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const float* I0,
-                                int32_t D, const int64_t* users, const int64_t* pos,
-                                const int64_t* neg, const float* dscore, const float* grad2,
-                                int64_t B, float* gU, float* gI, float* gU0, float* gI0,
-                                void* stream) {
+extern "C" int spex_bpr_bwd_ws_f32(const float* U, const float* I, const float* U0, const float* I0,
+                                   int32_t D, const int64_t* users, const int64_t* pos,
+                                   const int64_t* neg, const float* dscore, const float* grad2,
+                                   int64_t B, float* gU, float* gI, float* gU0, float* gI0, void* work,
+                                   int64_t work_bytes, void* stream) {
   SPEX_RETURN_IF(!U || !I || !U0 || !I0 || !users || !pos || !neg || !dscore || B < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(!gU || !gI || !gU0 || !gI0, SPEX_E_BADARG);
   SPEX_CHECK_TABLE(D);
@@ -509,22 +632,31 @@ extern "C" int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0,
   L.nseg = 2;
   L.idx[0] = users; L.src_idx[0] = pos; L.sign[0] = -1.f;
   L.idx[1] = users; L.src_idx[1] = neg; L.sign[1] = 1.f;
-  if ((rc = launch_scatter(L, I, gU, D, st))) return rc;
+  if ((rc = launch_scatter(L, I, gU, D, work, work_bytes, st))) return rc;
   // gI[pos] -= d*U[u];  gI[neg] += d*U[u]
   L.idx[0] = pos; L.src_idx[0] = users; L.sign[0] = -1.f;
   L.idx[1] = neg; L.src_idx[1] = users; L.sign[1] = 1.f;
-  if ((rc = launch_scatter(L, U, gI, D, st))) return rc;
+  if ((rc = launch_scatter(L, U, gI, D, work, work_bytes, st))) return rc;
   // ego tables: reg = 0.5*sum|.|^2 / B  ->  d/dx = x / B, times upstream grad2[1]
   L.coef = nullptr;
   L.gscalar = grad2 ? grad2 + 1 : nullptr;
   L.cconst = 1.f / (float)(B > 0 ? B : 1);
   L.nseg = 1;
   L.idx[0] = users; L.src_idx[0] = users; L.sign[0] = 1.f;
-  if ((rc = launch_scatter(L, U0, gU0, D, st))) return rc;
+  if ((rc = launch_scatter(L, U0, gU0, D, work, work_bytes, st))) return rc;
   L.nseg = 2;
   L.idx[0] = pos; L.src_idx[0] = pos; L.sign[0] = 1.f;
   L.idx[1] = neg; L.src_idx[1] = neg; L.sign[1] = 1.f;
-  return launch_scatter(L, I0, gI0, D, st);
+  return launch_scatter(L, I0, gI0, D, work, work_bytes, st);
+}
+
+extern "C" int spex_bpr_bwd_f32(const float* U, const float* I, const float* U0, const float* I0,
+                                int32_t D, const int64_t* users, const int64_t* pos,
+                                const int64_t* neg, const float* dscore, const float* grad2,
+                                int64_t B, float* gU, float* gI, float* gU0, float* gI0,
+                                void* stream) {
+  return spex_bpr_bwd_ws_f32(U, I, U0, I0, D, users, pos, neg, dscore, grad2, B, gU, gI, gU0, gI0, nullptr, 0,
+                             stream);
 }
 
 extern "C" int spex_adam_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr,

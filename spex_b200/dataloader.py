@@ -288,6 +288,23 @@ class LightTrainData(Dataset):
             return tm.contains(users, items)
         return np.fromiter(((int(u), int(j)) in tm for u, j in zip(users, items)), bool, len(users))
 
+    def ng_sample_device(self, graph, n_user_rows: int, seed: int = 2020):
+        """ng_sample() on the GPU: the epoch's (users, items, labels) as device tensors, negatives from
+        spex_sample_negatives against the device adjacency `graph` (same distribution as ng_sample, not the
+        same np.random stream - the exact-stream CPU path stays the parity oracle).  Returns the tensors
+        and also keeps them for arrays_device()."""
+        import torch
+
+        dev = graph.device
+        ps = torch.from_numpy(self._ps).to(dev)
+        neg = sample_negatives_device(graph.rowptr, graph.col, n_user_rows, self.num_item, ps[:, 0], self.num_ng,
+                                      seed)
+        users = torch.cat([ps[:, 0], ps[:, 0].repeat_interleave(self.num_ng)])
+        items = torch.cat([ps[:, 1], neg.reshape(-1)])
+        labels = torch.cat([torch.ones(ps.shape[0], device=dev), torch.zeros(neg.numel(), device=dev)])
+        self._device_arrays = (users, items, labels)
+        return self._device_arrays
+
     def ng_sample(self):
         n_pos = self._ps.shape[0]
         slots_u = np.repeat(self._ps[:, 0], self.num_ng)
@@ -390,6 +407,41 @@ def uniform_sample_bpr(train_users, train_items, n_users: int, m_items: int, n_s
         p[p == key.size] = 0
         todo = todo[key[p] == k] if key.size else todo[:0]
     return np.stack([users, pos, neg], axis=1)
+
+
+def sample_negatives_device(rowptr, col, n_user_rows: int, m_items: int, users, n_neg: int = 5, seed: int = 2020):
+    """GPU counterpart of LightTrainData.ng_sample's rejection loop (dataloader.py:250-265): for every
+    entry of `users` (int64, device) draw `n_neg` items uniformly among the items the user has NOT
+    interacted with -> int64 [n, n_neg].  (rowptr, col) is the device adjacency CSR whose user rows list
+    items as n_user_rows + item (spex_b200.ops.DeviceGraph; the hot flag in bit 31 is masked).
+    Counter-based randomness: deterministic in `seed`, independent of thread scheduling."""
+    import torch
+
+    from ._capi import call, ptr, stream_ptr
+
+    if not users.is_cuda:
+        raise RuntimeError("sample_negatives_device runs on sm_100a only (the CPU sampler is LightTrainData)")
+    users = users.to(torch.int64).contiguous()
+    out = torch.empty(users.numel(), n_neg, dtype=torch.int64, device=users.device)
+    call("spex_sample_negatives", ptr(rowptr), ptr(col), int(n_user_rows), int(m_items), ptr(users), users.numel(),
+         int(n_neg), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(out), stream_ptr())
+    return out
+
+
+def uniform_sample_bpr_device(rowptr, col, n_user_rows: int, m_items: int, n_users: int, n_samples: int,
+                              seed: int = 2020):
+    """GPU counterpart of uniform_sample_bpr: (users, pos, neg) int64 [n] each, on the device."""
+    import torch
+
+    from ._capi import call, ptr, stream_ptr
+
+    dev = rowptr.device
+    users = torch.empty(n_samples, dtype=torch.int64, device=dev)
+    pos = torch.empty_like(users)
+    neg = torch.empty_like(users)
+    call("spex_sample_bpr", ptr(rowptr), ptr(col), int(n_user_rows), int(m_items), int(n_users), int(n_samples),
+         int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(users), ptr(pos), ptr(neg), stream_ptr())
+    return users, pos, neg
 
 
 class SyntheticDataset(_GraphMixin, BasicDataset):

@@ -26,6 +26,66 @@ from ._capi import LongPlan, call, ptr, stream_ptr
 from .graph import CSRGraph, DEFAULT_SEG_LEN, plan_long_rows
 
 
+class _Workspaces:
+    """Persistent device scratch of the training step (at the 1B-edge size every
+    [N, D] fp32 temporary is 3.84 GB; the reference's autograd allocates and zero-fills several per
+    step).  Off by default (every call allocates, results never alias); the training loops switch
+    it on: the propagation ping-pong tables, the dense gradient table - zero-filled ONCE, afterwards
+    only the rows the last scatter touched are cleared - and the sort workspace are then reused."""
+
+    def __init__(self):
+        self.enabled = False
+        self.buf = {}
+        self.dirty = {}      # name -> list of int64 row-index tensors written since the buffer was zero
+
+    def get(self, name, shape, device, zero=False):
+        key = (name, tuple(shape), str(device))
+        t = self.buf.get(key) if self.enabled else None
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(*shape, dtype=torch.float32, device=device)
+            if self.enabled:
+                self.buf[key] = t
+                self.dirty[key] = []
+        elif zero:
+            D = shape[-1]
+            for rows in self.dirty[key]:
+                call("spex_clear_rows_f32", ptr(t), ptr(rows), rows.numel(), D, stream_ptr())
+            self.dirty[key] = []
+        return t, key
+
+    def mark(self, key, *row_lists):
+        if self.enabled and key in self.dirty:
+            self.dirty[key].extend(r for r in row_lists if r is not None and r.numel())
+
+    def clear(self):
+        self.buf.clear()
+        self.dirty.clear()
+
+
+workspaces = _Workspaces()
+
+
+def enable_persistent_workspaces(on: bool = True):
+    """Reuse the [N, D] scratch tables of the training step across steps (see _Workspaces)."""
+    workspaces.enabled = bool(on)
+    if not on:
+        workspaces.clear()
+
+
+def _scatter_workspace(total, device):
+    """Device workspace of the sorted scatter for `total` list entries (None: the scan form is used)."""
+    nbytes = int(call("spex_scatter_workspace_bytes", int(total)))
+    if nbytes == 0:
+        return None, 0
+    key = ("scatter_ws", str(device))
+    t = workspaces.buf.get(key) if workspaces.enabled else None
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if workspaces.enabled:
+            workspaces.buf[key] = t
+    return t, nbytes
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -378,9 +438,9 @@ class _PropagateMean(torch.autograd.Function):
         _need_cuda(table)
         E0 = _f32c(table)
         N, D = E0.shape
-        out = torch.empty_like(E0)
-        tmp0 = torch.empty_like(E0) if K >= 2 else None
-        tmp1 = torch.empty_like(E0) if K >= 3 else None
+        out = torch.empty_like(E0) if not workspaces.enabled else workspaces.get("prop_out", E0.shape, E0.device)[0]
+        tmp0 = workspaces.get("prop_tmp0", E0.shape, E0.device)[0] if K >= 2 else None
+        tmp1 = workspaces.get("prop_tmp1", E0.shape, E0.device)[0] if K >= 3 else None
         v = graph.val if val is None else val
         call("spex_propagate_mean_f32", ptr(graph.rowptr), ptr(graph.col), ptr(v), ptr(E0), N, D, K,
              ptr(out), ptr(tmp0), ptr(tmp1), graph.plan(D), stream_ptr())
@@ -392,9 +452,9 @@ class _PropagateMean(torch.autograd.Function):
         graph, K = ctx.graph, ctx.K
         g = _f32c(g)
         N, D = g.shape
-        dE0 = torch.empty_like(g)
-        tmp0 = torch.empty_like(g) if K >= 2 else None
-        tmp1 = torch.empty_like(g) if K >= 3 else None
+        dE0 = torch.empty_like(g) if not workspaces.enabled else workspaces.get("prop_dE0", g.shape, g.device)[0]
+        tmp0 = workspaces.get("prop_tmp0", g.shape, g.device)[0] if K >= 2 else None
+        tmp1 = workspaces.get("prop_tmp1", g.shape, g.device)[0] if K >= 3 else None
         call("spex_propagate_mean_bwd_f32", ptr(graph.rowptr), ptr(graph.col), ptr(ctx.valT), ptr(g),
              N, D, K, ptr(dE0), ptr(tmp0), ptr(tmp1), graph.plan(D), stream_ptr())
         return dE0, None, None, None, None
@@ -432,9 +492,11 @@ class _GatherDot(torch.autograd.Function):
         out, users, items = ctx.saved_tensors
         nur = ctx.n_user_rows
         D = out.shape[1]
-        g = torch.zeros_like(out)
-        call("spex_bce_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items),
-             ptr(_f32c(dgamma)), None, users.numel(), ptr(g[:nur]), ptr(g[nur:]), stream_ptr())
+        g, gkey = workspaces.get("grad_out", out.shape, out.device, zero=True)
+        work, wb = _scatter_workspace(users.numel(), out.device)
+        call("spex_bce_bwd_ws_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items),
+             ptr(_f32c(dgamma)), None, users.numel(), ptr(g[:nur]), ptr(g[nur:]), ptr(work), wb, stream_ptr())
+        workspaces.mark(gkey, users, items + nur)
         return g, None, None, None
 
 
@@ -464,10 +526,13 @@ class _BCELoss(torch.autograd.Function):
         out, users, items, dgamma = ctx.saved_tensors
         nur = ctx.n_user_rows
         D = out.shape[1]
-        g = torch.zeros_like(out)
+        # dense dL/d(out): zero except the rows of this batch (zero-filled once, see _Workspaces)
+        g, gkey = workspaces.get("grad_out", out.shape, out.device, zero=True)
         gl = _f32c(gloss.reshape(1))
-        call("spex_bce_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items), ptr(dgamma),
-             ptr(gl), users.numel(), ptr(g[:nur]), ptr(g[nur:]), stream_ptr())
+        work, wb = _scatter_workspace(users.numel(), out.device)
+        call("spex_bce_bwd_ws_f32", ptr(out[:nur]), ptr(out[nur:]), D, ptr(users), ptr(items), ptr(dgamma),
+             ptr(gl), users.numel(), ptr(g[:nur]), ptr(g[nur:]), ptr(work), wb, stream_ptr())
+        workspaces.mark(gkey, users, items + nur)
         return g, None, None, None, None
 
 
@@ -510,12 +575,15 @@ class _BPRLoss(torch.autograd.Function):
         out, table, users, pos, neg, dscore = ctx.saved_tensors
         nur = ctx.n_user_rows
         D = out.shape[1]
-        g = torch.zeros_like(out)
-        g0 = torch.zeros_like(table)
+        g, gkey = workspaces.get("grad_out", out.shape, out.device, zero=True)
+        g0, g0key = workspaces.get("grad_ego", table.shape, table.device, zero=True)
         grad2 = torch.stack([gloss.reshape(()), greg.reshape(())]).to(torch.float32).contiguous()
-        call("spex_bpr_bwd_f32", ptr(out[:nur]), ptr(out[nur:]), ptr(table[:nur]), ptr(table[nur:]), D,
+        work, wb = _scatter_workspace(2 * users.numel(), out.device)
+        call("spex_bpr_bwd_ws_f32", ptr(out[:nur]), ptr(out[nur:]), ptr(table[:nur]), ptr(table[nur:]), D,
              ptr(users), ptr(pos), ptr(neg), ptr(dscore), ptr(grad2), users.numel(), ptr(g[:nur]),
-             ptr(g[nur:]), ptr(g0[:nur]), ptr(g0[nur:]), stream_ptr())
+             ptr(g[nur:]), ptr(g0[:nur]), ptr(g0[nur:]), ptr(work), wb, stream_ptr())
+        workspaces.mark(gkey, users, pos + nur, neg + nur)
+        workspaces.mark(g0key, users, pos + nur, neg + nur)
         return g, g0, None, None, None, None
 
 
