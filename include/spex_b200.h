@@ -169,6 +169,23 @@ int spex_bce_bwd_ws_f32(const float* U, const float* I, int32_t D,
  * gradient buffer of the propagated table (N x D, 3.84 GB on the 1B-edge graph) is zero-filled
  * once, not every step (replaces the zeros_like of autograd's index backward, main_rec.py:35). */
 int spex_clear_rows_f32(float* table, const int64_t* rows, int64_t n, int32_t D, void* stream);
+/*
+ * Row-partitioned training (spex_b200/dist.py: PartitionedTrainer).
+ *   spex_gather_owned_rows_f32: R[i, :] = table_local[rows[i] - row_lo, :] if row_lo <= rows[i] < row_hi,
+ *       else 0 - every rank fills the rows of the batch it owns, a sum all-reduce of R then gives every
+ *       rank all of them (one non-zero term per row: exact).  Replaces all_users[users] / all_items[items]
+ *       (model.py:115-116) when the table is partitioned.
+ *   spex_scatter_rows_f32: out[dst_rows[b] - row_lo, :] = sum over b' with the same destination, ascending
+ *       b', of coef[b'] * (*gscalar) * cconst * src[src_rows[b'], :], only for destinations inside
+ *       [row_lo, row_hi) (row_hi == 0: all rows): the index backward of autograd (main_rec.py:35) restricted
+ *       to the rows a rank owns.  Same deterministic segmented reduction (and workspace) as spex_bce_bwd_ws_f32.
+ */
+int spex_gather_owned_rows_f32(const float* table_local, const int64_t* rows, int64_t n, int32_t D,
+                               int64_t row_lo, int64_t row_hi, float* R, void* stream);
+int spex_scatter_rows_f32(const int64_t* dst_rows, const int64_t* src_rows, const float* coef,
+                          const float* gscalar, float cconst, int64_t B, const float* src, int32_t D,
+                          float* out, int64_t row_lo, int64_t row_hi, void* work, int64_t work_bytes,
+                          void* stream);
 
 /*
  * BPR step (north_star addition; semantics of upstream LightGCN bpr_loss):

@@ -56,6 +56,8 @@ SIGNATURES = {
     "spex_scatter_workspace_bytes": (_i64, [_i64]),
     "spex_bce_bwd_ws_f32": (C.c_int, [_p, _p, _i32, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p]),
     "spex_clear_rows_f32": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "spex_gather_owned_rows_f32": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _p, _p]),
+    "spex_scatter_rows_f32": (C.c_int, [_p, _p, _p, _p, _f, _i64, _p, _i32, _p, _i64, _i64, _p, _i64, _p]),
     "spex_bpr_bwd_ws_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
     "spex_bpr_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "spex_bpr_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),

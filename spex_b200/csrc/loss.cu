@@ -99,7 +99,13 @@ struct ScatterList {
   const float* coef;     // per-sample [B] or NULL (=1)
   const float* gscalar;  // device scalar or NULL (=1)
   float cconst;
+  // optional row window (row partition across GPUs): only destination rows in [row_lo, row_hi) are
+  // written, at out[(row - row_lo), :]; row_hi == 0 means "all rows"
+  int64_t row_lo, row_hi;
 };
+__device__ __forceinline__ bool in_window(const ScatterList& L, int64_t row) {
+  return L.row_hi == 0 || (row >= L.row_lo && row < L.row_hi);
+}
 
 template <int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -110,6 +116,7 @@ scatter_rows_kernel(ScatterList L, const float* __restrict__ src, float* __restr
   if (t >= total) return;
   const int myseg = (int)(t / L.B);
   const int64_t my = L.idx[myseg][t - (int64_t)myseg * L.B];
+  if (!in_window(L, my)) return;
   const float gs = (L.gscalar ? L.gscalar[0] : 1.f) * L.cconst;
   float4 acc[NV];
 #pragma unroll
@@ -144,7 +151,7 @@ scatter_rows_kernel(ScatterList L, const float* __restrict__ src, float* __restr
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int d = (lane + 32 * v) * 4;
-    if (d < D) *reinterpret_cast<float4*>(out + my * D + d) = acc[v];
+    if (d < D) *reinterpret_cast<float4*>(out + (my - L.row_lo) * D + d) = acc[v];
   }
 }
 
@@ -175,6 +182,7 @@ scatter_sorted_kernel(ScatterList L, const uint32_t* __restrict__ keys, const ui
   if (p >= total) return;
   const uint32_t my = keys[p];
   if (p > 0 && keys[p - 1] == my) return;   // not the head of its row's run
+  if (!in_window(L, (int64_t)my)) return;
   const float gs = (L.gscalar ? L.gscalar[0] : 1.f) * L.cconst;
   float4 acc[NV];
 #pragma unroll
@@ -192,7 +200,7 @@ scatter_sorted_kernel(ScatterList L, const uint32_t* __restrict__ keys, const ui
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int d = (lane + 32 * v) * 4;
-    if (d < D) *reinterpret_cast<float4*>(out + (int64_t)my * D + d) = acc[v];
+    if (d < D) *reinterpret_cast<float4*>(out + ((int64_t)my - L.row_lo) * D + d) = acc[v];
   }
 }
 
@@ -247,6 +255,20 @@ static int launch_scatter(const ScatterList& L, const float* src, float* out, in
     scatter_rows_kernel<4><<<grid, kWarpsPerCta * 32, 0, st>>>(L, src, out, D);
   count_launch();
   return check_last();
+}
+
+// R[i, :] = table_local[rows[i] - row_lo, :] if rows[i] in [row_lo, row_hi) else 0  (thread per float4)
+__global__ void __launch_bounds__(256)
+gather_owned_rows_kernel(const float* __restrict__ table_local, const int64_t* __restrict__ rows, int64_t n,
+                         int D4, int64_t row_lo, int64_t row_hi, float* __restrict__ R) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n * D4; i += stride) {
+    const int64_t r = rows[i / D4];
+    float4 v = f4_zero();
+    if (r >= row_lo && r < row_hi) v = reinterpret_cast<const float4*>(table_local)[(r - row_lo) * D4 + (i % D4)];
+    reinterpret_cast<float4*>(R)[i] = v;
+  }
 }
 
 // out[rows[i], :] = 0  (thread per float4; duplicate rows are harmless)
@@ -556,6 +578,42 @@ extern "C" int spex_clear_rows_f32(float* table, const int64_t* rows, int64_t n,
   clear_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, rows, n, D / 4);
   count_launch();
   return check_last();
+}
+
+extern "C" int spex_gather_owned_rows_f32(const float* table_local, const int64_t* rows, int64_t n, int32_t D,
+                                          int64_t row_lo, int64_t row_hi, float* R, void* stream) {
+  SPEX_RETURN_IF(!table_local || !R || (n > 0 && !rows) || n < 0 || row_lo < 0 || row_hi < row_lo, SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(table_local) || !aligned16(R), SPEX_E_ALIGN);
+  if (n == 0) return 0;
+  int64_t blocks = (n * (D / 4) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  gather_owned_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table_local, rows, n, D / 4, row_lo,
+                                                                               row_hi, R);
+  count_launch();
+  return check_last();
+}
+
+extern "C" int spex_scatter_rows_f32(const int64_t* dst_rows, const int64_t* src_rows, const float* coef,
+                                     const float* gscalar, float cconst, int64_t B, const float* src, int32_t D,
+                                     float* out, int64_t row_lo, int64_t row_hi, void* work, int64_t work_bytes,
+                                     void* stream) {
+  SPEX_RETURN_IF(!dst_rows || !src_rows || !src || !out || B < 0 || row_lo < 0 || (row_hi != 0 && row_hi < row_lo),
+                 SPEX_E_BADARG);
+  SPEX_CHECK_TABLE(D);
+  SPEX_RETURN_IF(!aligned16(src) || !aligned16(out), SPEX_E_ALIGN);
+  ScatterList L{};
+  L.nseg = 1;
+  L.B = B;
+  L.idx[0] = dst_rows;
+  L.src_idx[0] = src_rows;
+  L.sign[0] = 1.f;
+  L.coef = coef;
+  L.gscalar = gscalar;
+  L.cconst = cconst;
+  L.row_lo = row_lo;
+  L.row_hi = row_hi;
+  return launch_scatter(L, src, out, D, work, work_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int spex_bce_bwd_ws_f32(const float* U, const float* I, int32_t D, const int64_t* users,

@@ -359,3 +359,217 @@ class PartitionedPropagator:
             done = torch.cuda.Event()
             done.record(self._side)
         self._staged = (self._key(next_E0_local), done)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Row-partitioned TRAINING: the step of main_rec.py:30-37 with the table, its
+# gradient and the Adam moments split by owner rank.
+#
+#   forward   out_p  = propagate(W_p)                      (the exchange above; rows [r0, r1) of the mean)
+#   batch     every rank holds the whole mini-batch (256 samples: replicated host-side sampling with a
+#             shared seed, no communication).  The <= 2B rows of `out` the batch touches are assembled
+#             on every rank: each rank fills the rows it owns into a compact [2B, D] buffer, zeros
+#             elsewhere, one sum all-reduce (a single non-zero term per row: exact, order-free)
+#   loss      BCE on the compact rows, replicated: bit-identical to the single-GPU loss
+#   backward  dL/d(out) rows are scattered by the same deterministic segmented reduction, each rank
+#             keeping only the rows it owns (row window), into its [rows_p, D] gradient slice;
+#             dL/dW = (1/(K+1)) sum_k (A^T)^k dL/d(out) = propagate(dL/d(out)) because the normalised
+#             adjacency is symmetric: the SAME partitioned propagation, exchange included, on gradients
+#             (sum-of-powers instead of the single-GPU kernel's Horner form: <= 1e-6 relative, not
+#             bit-equal).  Edge dropout (non-symmetric values) is not supported in this mode.
+#   optimiser row-owned dense Adam (spex_adam_f32 on the local slice): no collective.
+# ---------------------------------------------------------------------------------------------------
+class _CudaTrainOps:
+    """The CUDA entry points behind PartitionedTrainer (no fallback: CPU tensors are rejected)."""
+
+    def gather_owned(self, local, rows, r0, r1):
+        from ._capi import call, ptr, stream_ptr
+
+        R = torch.empty(rows.numel(), local.shape[1], dtype=torch.float32, device=local.device)
+        call("spex_gather_owned_rows_f32", ptr(local), ptr(rows), rows.numel(), local.shape[1], r0, r1, ptr(R),
+             stream_ptr())
+        return R
+
+    def bce(self, Ru, Ri, labels):
+        from ._capi import call, ptr, stream_ptr
+
+        B, D = Ru.shape
+        ar = torch.arange(B, device=Ru.device)
+        gamma = torch.empty(B, dtype=torch.float32, device=Ru.device)
+        dgamma = torch.empty_like(gamma)
+        loss = torch.empty(1, dtype=torch.float32, device=Ru.device)
+        call("spex_bce_fwd_f32", ptr(Ru), ptr(Ri), D, ptr(ar), ptr(ar), ptr(labels), B, ptr(gamma), ptr(loss),
+             ptr(dgamma), stream_ptr())
+        return loss, dgamma
+
+    def scatter(self, dst_rows, src, coef, out_local, r0, r1):
+        from . import ops
+        from ._capi import call, ptr, stream_ptr
+
+        B, D = src.shape
+        ar = torch.arange(B, device=src.device)
+        work, wb = ops._scatter_workspace(B, src.device)
+        call("spex_scatter_rows_f32", ptr(dst_rows), ptr(ar), ptr(coef), None, 1.0, B, ptr(src), D, ptr(out_local),
+             r0, r1, ptr(work), wb, stream_ptr())
+
+    def clear_rows(self, table_local, rows_local):
+        from ._capi import call, ptr, stream_ptr
+
+        if rows_local.numel():
+            call("spex_clear_rows_f32", ptr(table_local), ptr(rows_local), rows_local.numel(), table_local.shape[1],
+                 stream_ptr())
+
+    def adam(self, W, g, m, v, lr, b1, b2, eps, step):
+        from . import ops
+
+        ops.adam_step(W, g, m, v, lr, b1, b2, eps, step)
+
+
+class _TorchTrainOps:
+    """The same five operations in plain torch: used by the gloo CPU test of the orchestration (the
+    oracle's arithmetic; never selected on a GPU)."""
+
+    def gather_owned(self, local, rows, r0, r1):
+        R = torch.zeros(rows.numel(), local.shape[1], dtype=local.dtype)
+        own = (rows >= r0) & (rows < r1)
+        R[own] = local[rows[own] - r0]
+        return R
+
+    def bce(self, Ru, Ri, labels):
+        gamma = (Ru * Ri).sum(1)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(gamma, labels).reshape(1)
+        return loss, (torch.sigmoid(gamma) - labels) / labels.numel()
+
+    def scatter(self, dst_rows, src, coef, out_local, r0, r1):
+        own = (dst_rows >= r0) & (dst_rows < r1)
+        out_local.index_add_(0, dst_rows[own] - r0, src[own] * coef[own, None])
+
+    def clear_rows(self, table_local, rows_local):
+        table_local[rows_local] = 0
+
+    def adam(self, W, g, m, v, lr, b1, b2, eps, step):
+        m.lerp_(g, 1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = v.sqrt() / (1 - b2 ** step) ** 0.5 + eps
+        W.addcdiv_(m, denom, value=-lr / (1 - b1 ** step))
+
+
+class PartitionedTrainer:
+    """main_rec.py:30-37 over a row partition: this rank owns rows [r0, r1) of the fused table `W_local`,
+    of its gradient and of the Adam moments.  `prop` is the PartitionedPropagator of the same partition."""
+
+    def __init__(self, prop: PartitionedPropagator, W_local: torch.Tensor, n_user_rows: int, lr: float = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, train_ops=None):
+        self.prop = prop
+        self.W = W_local
+        self.nur = int(n_user_rows)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.m = torch.zeros_like(W_local)
+        self.v = torch.zeros_like(W_local)
+        self.g = torch.zeros_like(W_local)        # dL/d(out), zero except the batch's owned rows
+        self.dW = torch.empty_like(W_local)
+        self.out = torch.empty_like(W_local)
+        self._dirty = None
+        self.t = 0
+        self.ops = train_ops if train_ops is not None else _CudaTrainOps()
+
+    def step(self, users: torch.Tensor, items: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        p, r0, r1 = self.prop, self.prop.r0, self.prop.r1
+        out = p.propagate(self.W, out=self.out)
+        B = users.numel()
+        rows = torch.cat([users, items + self.nur]).to(torch.int64)
+        R = self.ops.gather_owned(out, rows, r0, r1)
+        if p.world > 1:
+            dist.all_reduce(R, group=p.group)
+        Ru, Ri = R[:B], R[B:]
+        loss, dgamma = self.ops.bce(Ru, Ri, labels.to(torch.float32))
+        if self._dirty is not None:
+            self.ops.clear_rows(self.g, self._dirty)
+        self.ops.scatter(rows[:B], Ri, dgamma, self.g, r0, r1)      # gU[users] = sum dgamma * I[items]
+        self.ops.scatter(rows[B:], Ru, dgamma, self.g, r0, r1)      # gI[items] = sum dgamma * U[users]
+        own = (rows >= r0) & (rows < r1)
+        self._dirty = (rows[own] - r0).contiguous()
+        dW = p.propagate(self.g, out=self.dW)                        # (1/(K+1)) sum_k A^k g
+        self.t += 1
+        self.ops.adam(self.W, dW, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t)
+        return loss
+
+    def gather_table(self, local: torch.Tensor) -> torch.Tensor:
+        """The full [N, D] table from the ranks' slices (evaluation: every rank ranks its own users
+        against all items)."""
+        full = torch.empty(self.prop.N, local.shape[1], dtype=local.dtype, device=local.device)
+        self.prop._all_gather_rows(full, local)
+        return full
+
+
+# ---------------------------------------------------------------------------------------------------
+# Evaluation sharded by user (SURVEY §8e row 4): no data-path communication, one all-reduce of sums.
+# ---------------------------------------------------------------------------------------------------
+def shard_range(n: int, rank: int, world: int):
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+class ShardedEvaluator:
+    """Full-ranking top-k + Recall/NDCG over a user shard per rank.  The propagated item table is
+    replicated (5 M x 64 fp16 = 640 MB), every rank ranks users [lo, hi) of the list it is given with the
+    tcgen05 scorer, metrics are summed over ranks with ONE all-reduce of three numbers."""
+
+    def __init__(self, U_all, I_all, mask_rowptr=None, mask_col=None, k: int = 20, group=None, scorer: str = "f16"):
+        from . import ops
+
+        self.U, self.I = U_all, I_all
+        self.mrp, self.mcol = mask_rowptr, mask_col
+        self.k, self.group, self.scorer = int(k), group, scorer
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.D = I_all.shape[1]
+        if scorer == "f16":
+            self.Ih, self.m_pad, self.imeta = ops.pack_f16(I_all, None, ops.TC_ITEM_MULTIPLE)
+        elif scorer == "bf16":
+            self.Ib, self.m_pad = ops.pack_bf16(I_all, None, ops.TC_ITEM_MULTIPLE)
+        elif scorer != "fp32":
+            raise ValueError("scorer must be 'f16', 'bf16' or 'fp32'")
+
+    def rank_topk(self, users: torch.Tensor, block: int = 148 * 2 * 128 * 4):
+        """(idx int32 [n_local, k], val fp32 [n_local, k], (lo, hi)) for this rank's shard of `users`."""
+        from . import ops
+
+        lo, hi = shard_range(users.numel(), self.rank, self.world)
+        mine = users[lo:hi].to(torch.int64).contiguous()
+        dev = self.I.device
+        idx = torch.empty(hi - lo, self.k, dtype=torch.int32, device=dev)
+        val = torch.empty(hi - lo, self.k, dtype=torch.float32, device=dev)
+        m = self.I.shape[0]
+        for a in range(0, hi - lo, block):
+            ub = mine[a: a + block]
+            o_i, o_v = idx[a: a + ub.numel()], val[a: a + ub.numel()]
+            if self.scorer == "f16":
+                Uh, b_pad, umeta = ops.pack_f16(self.U, ub, ops.TC_USER_MULTIPLE)
+                ops.score_topk_f16(Uh, umeta, ub.numel(), b_pad, self.Ih, self.imeta, m, self.m_pad, self.D, self.k,
+                                   ub, self.mrp, self.mcol, o_i, o_v)
+            elif self.scorer == "bf16":
+                Ub, b_pad = ops.pack_bf16(self.U, ub, ops.TC_USER_MULTIPLE)
+                ops.score_topk_bf16(Ub, ub.numel(), b_pad, self.Ib, m, self.m_pad, self.k, ub, self.mrp, self.mcol,
+                                    o_i, o_v)
+            else:
+                i32, v32 = ops.score_topk_f32(self.U, self.I, ub, self.k, self.mrp, self.mcol)
+                o_i.copy_(i32)
+                o_v.copy_(v32)
+        return idx, val, (lo, hi)
+
+    def recall_ndcg(self, users: torch.Tensor, truth_rowptr, truth_col):
+        """Mean Recall@k / NDCG@k over ALL of `users` (truth: CSR over the positions of `users`): local
+        metrics on the host, one all-reduce of (sum recall, sum ndcg, count)."""
+        from . import metrics
+
+        idx, _, (lo, hi) = self.rank_topk(users)
+        trp = np.asarray(truth_rowptr)
+        rec, ndcg = metrics.fullrank_recall_ndcg(idx.cpu().numpy(), trp[lo: hi + 1] - trp[lo],
+                                                 np.asarray(truth_col)[trp[lo]: trp[hi]], self.k)
+        s = torch.tensor([float(rec.sum()), float(ndcg.sum()), float(hi - lo)], dtype=torch.float64,
+                         device=self.I.device if dist.is_initialized() and dist.get_backend(self.group) == "nccl"
+                         else "cpu")
+        if self.world > 1:
+            dist.all_reduce(s, group=self.group)
+        n = max(float(s[2]), 1.0)
+        return {"recall": float(s[0]) / n, "ndcg": float(s[1]) / n, "users": int(s[2])}

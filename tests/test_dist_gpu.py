@@ -112,3 +112,102 @@ def test_partitioned_propagation_matches_single_gpu():
             # the row partition does not change any row's summation order: bit-identical
             assert exact and reproducible, (rank, key)
             assert "layer3" in phases and "e0_exchange" in phases
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from helpers import make_args
+        from spex_b200 import ops
+        from spex_b200.dataloader import SyntheticDataset
+        from spex_b200.dist import PartitionedPropagator, PartitionedTrainer, ShardedEvaluator
+        from spex_b200.graph import partition_rows_by_nnz
+        from spex_b200.model import LightGCN
+        from spex_b200.optim import FusedAdam
+
+        # single-GPU reference on THIS rank: the drop-in model + FusedAdam, three steps
+        ds = SyntheticDataset(400, 250, 6000, seed=4)
+        torch.manual_seed(2020)
+        model = LightGCN(make_args(), ds).to(dev)
+        W0 = model._table.detach().clone()
+        opt = FusedAdam(model.parameters(), lr=1e-2)
+        rng = np.random.default_rng(0)
+        batches, ref_losses = [], []
+        for _ in range(3):
+            users = torch.from_numpy(rng.integers(0, ds.n_users, 256)).to(dev)
+            users[:40] = users[0]
+            items = torch.from_numpy(rng.integers(0, ds.m_items, 256)).to(dev)
+            labels = torch.from_numpy(rng.integers(0, 2, 256)).float().to(dev)
+            batches.append((users, items, labels))
+            model.train()
+            opt.zero_grad(set_to_none=True)
+            loss = model(users, items, labels, flag=0)
+            loss.backward()
+            opt.step()
+            ref_losses.append(float(loss))
+        W_ref = model._table.detach().clone()
+        # partitioned run over the ranks
+        full = model.device_graph()
+        g_host = ds.getCSR()
+        N, D, K = full.n_rows, 64, 3
+        bounds = partition_rows_by_nnz(g_host.rowptr, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        lo, hi = int(g_host.rowptr[r0]), int(g_host.rowptr[r1])
+        lg = ops.DeviceGraph((full.rowptr[r0: r1 + 1] - lo).contiguous(), full.col[lo:hi].clone(),
+                             full.val[lo:hi].clone(), N, None, full.seg_len, row_offset=r0)
+        res = {}
+        for mode in ("nccl", "push"):
+            prop = PartitionedPropagator(lg, bounds, D, K, mode=mode, device=dev)
+            if mode == "push":
+                prop.e0_exchange = "push"
+            tr = PartitionedTrainer(prop, W0[r0:r1].clone(), ds.n_users + 1, lr=1e-2)
+            losses = [float(tr.step(*b)) for b in batches]
+            werr = float((tr.W - W_ref[r0:r1]).abs().max() / W_ref.abs().max())
+            res[mode] = (losses[0] == ref_losses[0], max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)), werr)
+            prop.close()
+        # evaluation sharded by user against the single-GPU ranking
+        model.eval()
+        users_all = torch.arange(ds.n_users, device=dev)
+        i_ref, v_ref = model.rank_topk(users_all, k=20, precision="f16")
+        au, ai = model.computer()
+        mrp, mcol = model.train_mask_csr()
+        ev = ShardedEvaluator(au, ai, mrp, mcol, k=20)
+        idx, val, (a, b) = ev.rank_topk(users_all)
+        same = bool(torch.equal(idx, i_ref[a:b]) and torch.equal(val, v_ref[a:b]))
+        tu = np.array([u for u in range(ds.n_users) if u in ds.testRatings for _ in ds.testRatings[u]], np.int64)
+        ti = np.array([i for u in range(ds.n_users) if u in ds.testRatings for i in ds.testRatings[u]], np.int64)
+        from spex_b200 import metrics
+        from spex_b200.graph import build_interaction_csr
+        trp, tcol = build_interaction_csr(tu, ti, ds.n_users, ds.m_items)
+        mm = ev.recall_ndcg(users_all, trp, tcol)
+        r1g, n1g = metrics.fullrank_recall_ndcg(i_ref.cpu().numpy(), trp, tcol, 20)
+        res["eval"] = (same, abs(mm["recall"] - float(r1g.mean())), abs(mm["ndcg"] - float(n1g.mean())))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_training_and_sharded_eval_match_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        for mode in ("nccl", "push"):
+            first_equal, lerr, werr = res[mode]
+            assert first_equal, (rank, mode)             # same arithmetic on the assembled rows: bit-equal loss
+            assert lerr < 1e-5 and werr < 1e-5, (rank, mode, lerr, werr)
+        same, dr, dn = res["eval"]
+        assert same and dr < 1e-12 and dn < 1e-12, (rank, res["eval"])
