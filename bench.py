@@ -782,10 +782,16 @@ def run_ours(args):
                  "scorer": args.eval_scorer, "check": {"ok": eval_ok, "top20_ids_equal_to_fp32_scorer": agree},
                  "config": {"workload": f"full-ranking top-20 sweep, {n_total} users x {m} items, D={D}, user-sharded x{world} "
                                         "(BASELINE.json configs[4])"},
+                 # B200_PROFILING.md: the burst peak is for a kernel timed alone, the sustained one for a kernel
+                 # timed inside a long step - a sweep of seconds runs under the power cap like the sustained GEMM
                  "roofline": {"bound": "tensor", "kernel": "score_topk_f16_kernel<64,1>" if args.eval_scorer == "f16"
-                              else "score_topk_tc_kernel<1>", "achieved": tf, "peak": tc_burst, "unit": "TFLOP/s",
-                              "frac": tf / tc_burst, "peak_kind": peak_kind,
-                              "frac_of_sustained_peak": tf / tc_sust, "traffic": None},
+                              else "score_topk_tc_kernel<1>", "achieved": tf,
+                              "peak": tc_sust if ms_ev > 1000.0 else tc_burst, "unit": "TFLOP/s",
+                              "frac": tf / (tc_sust if ms_ev > 1000.0 else tc_burst),
+                              "peak_kind": peak_kind + (" (sustained bf16 GEMM: the sweep runs for seconds)"
+                                                        if ms_ev > 1000.0 else " (burst bf16 GEMM)"),
+                              "frac_of_burst_peak": tf / tc_burst, "frac_of_sustained_peak": tf / tc_sust,
+                              "traffic": None},
                  "cpu_baseline": cpu_eval}
         del idx, val, users
         if world > 1:
@@ -795,6 +801,37 @@ def run_ours(args):
     trainj = None
     if world == 1 and not args.no_train:
         trainj = bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, peak_kind, dev)
+    elif world > 1 and not args.no_train:
+        # row-partitioned training step (spex_b200/dist.py: PartitionedTrainer): table / gradient / Adam
+        # moments owned by row, the batch replicated (same seed on every rank), backward = the same
+        # partitioned propagation applied to the gradient
+        from spex_b200.dist import PartitionedTrainer
+
+        tr = PartitionedTrainer(prop, E0_local.clone(), nur, lr=1e-3)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(11)
+        Bt = args.train_batch
+        tu = torch.randint(0, nu, (Bt,), device=dev, generator=gen)
+        ti = torch.randint(0, m, (Bt,), device=dev, generator=gen)
+        tl = (torch.rand(Bt, device=dev, generator=gen) < (1.0 / 6.0)).float()
+        for _ in range(2):
+            tr.step(tu, ti, tl)
+        barrier()
+        n_tr = 4
+        ev0.record()
+        for _ in range(n_tr):
+            tloss = tr.step(tu, ti, tl)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_tr = float(t.item()) / n_tr
+        trainj = {"metric": "lightgcn_train_step_ms", "value": ms_tr, "unit": "ms", "higher_is_better": False,
+                  "steps_per_s": 1e3 / ms_tr, "batch": Bt, "loss": float(tloss.item()),
+                  "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * nnz / (ms_tr * 1e-3) / 1e9,
+                  "config": {"workload": f"main_rec.py:30-37 step, row-partitioned x{world}: forward + BCE + backward "
+                                         f"(partitioned propagation of the gradient) + row-owned Adam, exchange={args.exchange}"}}
+        del tr
 
     launches_total = _capi.launch_count() - launches0
     ck = clocks.stop() if clocks else None
