@@ -354,6 +354,28 @@ int spex_ngcf_epilogue_f32(const float* ego, const float* side, const float* W1,
                            void* stream);
 
 /*
+ * NGCF layer for TRAINING (NGCF_SPEX/code/main_rec.py:76-82 and its autograd), D == 64.
+ *   fwd: hd = (lrelu(side W1^T + b1) + lrelu((ego*side) W2^T + b2)) * mask   (mask NULL = 1: the 0 / 1/(1-p)
+ *        pattern of nn.Dropout, main_rec.py:81, drawn by the caller with the reference's RNG call);
+ *        norm = hd / max(|hd|, 1e-12) written with row stride norm_stride (concat buffer, main_rec.py:82-85).
+ *   bwd: d_hd_next = dL/d(hd) from the next layer (NULL for the last), d_norm = dL/d(norm) with its row
+ *        stride; writes d_ego, d_side [n, 64] and the weight / bias gradients.  The weight gradients are
+ *        reduced deterministically (fixed tile order per CTA, CTA partials summed in CTA order):
+ *        work = fp32 [SPEX_NGCF_BWD_BLOCKS * SPEX_NGCF_BWD_WORK_PER_BLOCK] workspace.
+ */
+#define SPEX_NGCF_BWD_BLOCKS 296
+#define SPEX_NGCF_BWD_WORK_PER_BLOCK 8320
+int spex_ngcf_layer_fwd_f32(const float* ego, const float* side, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* mask, int64_t n, int32_t D,
+                            float negative_slope, float* hd, float* norm, int64_t norm_stride,
+                            void* stream);
+int spex_ngcf_layer_bwd_f32(const float* ego, const float* side, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* mask, const float* d_hd_next,
+                            const float* d_norm, int64_t d_norm_stride, int64_t n, int32_t D,
+                            float negative_slope, float* d_ego, float* d_side, float* dW1, float* db1,
+                            float* dW2, float* db2, float* work, void* stream);
+
+/*
  * CUDA-IPC helpers for the row-partitioned multi-GPU path: each rank allocates its
  * exchange buffer with spex_ipc_alloc, publishes the 64-byte handle, and opens its peers'.
  * spex_spmm_csr_f32_push is spex_spmm_csr_f32 whose Y epilogue also stores every output row

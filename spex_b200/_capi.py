@@ -74,6 +74,9 @@ SIGNATURES = {
     "spex_score_topk_f16": (C.c_int, [_p, _p, _i32, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
     "spex_score_candidates_f32": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p]),
     "spex_ngcf_epilogue_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _f, _p, _p, _i64, _p]),
+    "spex_ngcf_layer_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _f, _p, _p, _i64, _p]),
+    "spex_ngcf_layer_bwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _f, _p, _p, _p, _p,
+                                          _p, _p, _p, _p]),
     "spex_ipc_alloc": (C.c_int, [_i64, C.POINTER(_p), _p]),
     "spex_ipc_open": (C.c_int, [_p, C.POINTER(_p)]),
     "spex_ipc_close": (C.c_int, [_p]),

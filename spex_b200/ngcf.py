@@ -11,8 +11,12 @@ names, forward(user, item, labels_list, flag)) and utility/load_data.py::Data.cr
 
 Inference (no gradient needed) runs the CSR SpMM + the fused `spex_ngcf_epilogue_f32` kernel that
 writes the normalised rows straight into the concat buffer.  When gradients are needed the same SpMM
-is used through an autograd function (backward = SpMM with the transposed values) and the dense
-64x64 part is composed from torch ops (library GEMMs on [N,64]x[64,64]: not a hot spot).
+is used through an autograd function (backward = SpMM with the transposed values) and the dense part of
+the layer - both 64x64 products, leaky-relu, message dropout, L2 normalisation - is ONE kernel forward
+(`spex_ngcf_layer_fwd_f32`) and one backward (`spex_ngcf_layer_bwd_f32`, weight gradients reduced in a
+fixed order, no atomics): no cuBLAS / ATen elementwise op on the training path.
+Scoring: `rate_all_items` (the dense [B, n_items] matrix of utility/batch_test.py:158) and `rank_topk`
+(the same contraction on the tcgen05 scorer at D = 128, fused with mask + top-k).
 The user table keeps the reference's extra padding row, dropped in forward (main_rec.py:73).
 There is no CPU fallback: every op raises on a CPU tensor.
 """
@@ -166,10 +170,15 @@ class Model_Wrapper(nn.Module):
             embs = [ego]
             for i in range(L):
                 side = _SpMM.apply(ego, graph, graph_t)
-                s = F.leaky_relu(self.GC_Linear_list[i](side), self.negative_slope)
-                b = F.leaky_relu(self.Bi_Linear_list[i](ego * side), self.negative_slope)
-                ego = self.dropout_list[i](s + b)
-                embs.append(F.normalize(ego, p=2, dim=1))
+                # message dropout (main_rec.py:81): the mask comes from the reference's own RNG call - the
+                # nn.Dropout module applied to a tensor of the layer's shape - and is applied inside the kernel
+                mask = None
+                if self.training and self.mess_dropout[i] > 0:
+                    mask = self.dropout_list[i](torch.ones_like(side))
+                ego, norm = ops.ngcf_layer(ego, side, self.GC_Linear_list[i].weight, self.GC_Linear_list[i].bias,
+                                           self.Bi_Linear_list[i].weight, self.Bi_Linear_list[i].bias, mask,
+                                           self.negative_slope)
+                embs.append(norm)
             all_embeddings = torch.cat(embs, dim=1)
         return torch.split(all_embeddings, [self.n_users, self.n_items], dim=0)
 
@@ -188,6 +197,22 @@ class Model_Wrapper(nn.Module):
         predict = torch.sum(torch.mul(u_g_embeddings, i_g_embeddings), dim=1)
         real = torch.as_tensor(labels_list, device=predict.device).float()
         return self.rec_loss_function(predict, real)
+
+    @torch.no_grad()
+    def rank_topk(self, users, k: int = 20, mask_rowptr=None, mask_col=None, precision: str = "f16"):
+        """Top-k items per user over the concatenated layer outputs (utility/batch_test.py:158 followed by
+        the ranking): tcgen05 fp16-accumulator filter + exact fp32 re-score at D = 64 (L + 1), or the exact
+        fp32 CUDA-core scorer (precision "fp32").  Returns (idx int32 [B, k], score fp32 [B, k])."""
+        ua, ia = self.propagate()
+        ua, ia = ua.contiguous(), ia.contiguous()
+        users = torch.as_tensor(users, device=ua.device).long().contiguous()
+        Dk = ua.shape[1]
+        if precision == "fp32" or Dk not in (64, 128):
+            return ops.score_topk_f32(ua, ia, users, k, mask_rowptr, mask_col)
+        Ih, m_pad, imeta = ops.pack_f16(ia, None, ops.TC_ITEM_MULTIPLE)
+        Uh, b_pad, umeta = ops.pack_f16(ua, users, ops.TC_USER_MULTIPLE)
+        return ops.score_topk_f16(Uh, umeta, users.numel(), b_pad, Ih, imeta, ia.shape[0], m_pad, Dk, k, users,
+                                  mask_rowptr, mask_col)
 
     @torch.no_grad()
     def rate_all_items(self, users):

@@ -779,5 +779,52 @@ def ngcf_epilogue(ego, side, W1, b1, W2, b2, negative_slope, out=None, norm=None
     return out
 
 
+NGCF_BWD_BLOCKS = 296            # SPEX_NGCF_BWD_BLOCKS in include/spex_b200.h
+NGCF_BWD_WORK_PER_BLOCK = 8320   # SPEX_NGCF_BWD_WORK_PER_BLOCK
+
+
+class _NGCFLayer(torch.autograd.Function):
+    """One NGCF layer after the SpMM (NGCF_SPEX/code/main_rec.py:77-82) on the library's kernels:
+    (hd, norm) = f(ego, side; W1, b1, W2, b2, mask) with its hand-written backward (deterministic weight
+    gradients).  `mask` is nn.Dropout's 0 / 1/(1-p) pattern (None: no dropout)."""
+
+    @staticmethod
+    def forward(ctx, ego, side, W1, b1, W2, b2, mask, slope):
+        _need_cuda(ego, side, W1, W2)
+        ego, side, W1, W2 = _f32c(ego), _f32c(side), _f32c(W1), _f32c(W2)
+        n, D = ego.shape
+        hd = torch.empty_like(ego)
+        norm = torch.empty_like(ego)
+        call("spex_ngcf_layer_fwd_f32", ptr(ego), ptr(side), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(mask), n, D,
+             float(slope), ptr(hd), ptr(norm), D, stream_ptr())
+        ctx.save_for_backward(ego, side, W1, b1, W2, b2, mask)
+        ctx.slope = float(slope)
+        return hd, norm
+
+    @staticmethod
+    def backward(ctx, g_hd, g_norm):
+        ego, side, W1, b1, W2, b2, mask = ctx.saved_tensors
+        n, D = ego.shape
+        dev = ego.device
+        d_ego, d_side = torch.empty_like(ego), torch.empty_like(side)
+        dW1, dW2 = torch.empty_like(W1), torch.empty_like(W2)
+        db1 = torch.empty(D, dtype=torch.float32, device=dev)
+        db2 = torch.empty(D, dtype=torch.float32, device=dev)
+        work = torch.empty(NGCF_BWD_BLOCKS * NGCF_BWD_WORK_PER_BLOCK, dtype=torch.float32, device=dev)
+        g_hd = None if g_hd is None else _f32c(g_hd)
+        g_norm = None if g_norm is None else _f32c(g_norm)
+        if g_hd is None and g_norm is None:
+            g_norm = torch.zeros_like(ego)
+        call("spex_ngcf_layer_bwd_f32", ptr(ego), ptr(side), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(mask),
+             ptr(g_hd), ptr(g_norm), D, n, D, ctx.slope, ptr(d_ego), ptr(d_side), ptr(dW1), ptr(db1), ptr(dW2),
+             ptr(db2), ptr(work), stream_ptr())
+        return d_ego, d_side, dW1, (db1 if b1 is not None else None), dW2, (db2 if b2 is not None else None), None, None
+
+
+def ngcf_layer(ego, side, W1, b1, W2, b2, mask=None, negative_slope: float = 0.01):
+    """(hd, norm) of one NGCF layer given side = A . ego; differentiable (see _NGCFLayer)."""
+    return _NGCFLayer.apply(ego, side, W1, b1, W2, b2, mask, negative_slope)
+
+
 def launch_count() -> int:
     return _capi.launch_count()

@@ -118,3 +118,60 @@ def test_gpu_ngcf_loss_and_gradients(G, graph, cuda_device):
         assert rel_err(got.cpu(), torch.from_numpy(G[name])) < 1e-4, name
     assert rel_err(model.user_embedding.weight.grad.cpu()[::29], torch.from_numpy(G["grad_user_rows_29"])) < 1e-4
     assert rel_err(model.item_embedding.weight.grad.cpu()[::29], torch.from_numpy(G["grad_item_rows_29"])) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_ngcf_layer_kernels_match_torch_composition_with_dropout(G, graph, cuda_device):
+    """spex_ngcf_layer_fwd/bwd_f32 against the reference layer written with torch ops
+    (NGCF_SPEX/code/main_rec.py:77-82) on the same dropout mask: outputs and every gradient, and the
+    weight gradients bit-reproducible."""
+    import torch.nn.functional as F
+
+    from spex_b200 import ops
+
+    torch.manual_seed(0)
+    n, D = 5000, 64
+    dev = cuda_device
+    ego = (torch.randn(n, D, device=dev) * 0.2).requires_grad_(True)
+    side = (torch.randn(n, D, device=dev) * 0.2).requires_grad_(True)
+    W1 = (torch.randn(D, D, device=dev) * 0.2).requires_grad_(True)
+    W2 = (torch.randn(D, D, device=dev) * 0.2).requires_grad_(True)
+    b1 = (torch.randn(D, device=dev) * 0.1).requires_grad_(True)
+    b2 = (torch.randn(D, device=dev) * 0.1).requires_grad_(True)
+    mask = F.dropout(torch.ones(n, D, device=dev), 0.1, True)
+    g_hd = torch.randn(n, D, device=dev)
+    g_norm = torch.randn(n, D, device=dev)
+
+    def ref():
+        h = F.leaky_relu(F.linear(side, W1, b1)) + F.leaky_relu(F.linear(ego * side, W2, b2))
+        hd = h * mask
+        return hd, F.normalize(hd, p=2, dim=1)
+
+    params = (ego, side, W1, b1, W2, b2)
+    hd_r, nr_r = ref()
+    gr = torch.autograd.grad((hd_r * g_hd).sum() + (nr_r * g_norm).sum(), params)
+    hd, nr = ops.ngcf_layer(ego, side, W1, b1, W2, b2, mask, 0.01)
+    gg = torch.autograd.grad((hd * g_hd).sum() + (nr * g_norm).sum(), params)
+    assert rel_err(hd, hd_r) < 1e-5 and rel_err(nr, nr_r) < 1e-5
+    for name, a, b in zip(("ego", "side", "W1", "b1", "W2", "b2"), gg, gr):
+        assert rel_err(a, b) < 2e-5, name
+    hd2, nr2 = ops.ngcf_layer(ego, side, W1, b1, W2, b2, mask, 0.01)
+    gg2 = torch.autograd.grad((hd2 * g_hd).sum() + (nr2 * g_norm).sum(), params)
+    assert all(torch.equal(a, b) for a, b in zip(gg, gg2))
+
+
+@pytest.mark.gpu
+def test_gpu_ngcf_rank_topk_d128(G, graph, cuda_device):
+    """utility/batch_test.py:158 + ranking on the tcgen05 scorer at D = 128 against the dense matmul."""
+    model = _model(G, graph, cuda_device)
+    model.eval()
+    users = torch.arange(0, 300, device=cuda_device)
+    idx, val = model.rank_topk(users, k=20)
+    i32, v32 = model.rank_topk(users, k=20, precision="fp32")
+    scale = float(v32.abs().max())
+    assert float((val - v32).abs().max()) <= 2e-3 * scale
+    same = [(len(set(a.tolist()) & set(b.tolist())) / 20.0) for a, b in zip(idx.cpu().numpy(), i32.cpu().numpy())]
+    assert np.mean(same) > 0.97
+    dense = model.rate_all_items(users)
+    ref_idx = torch.topk(dense, 20, dim=1).indices
+    assert float((ref_idx == i32.long()).float().mean()) > 0.99
