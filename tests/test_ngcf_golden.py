@@ -170,8 +170,10 @@ def test_gpu_ngcf_rank_topk_d128(G, graph, cuda_device):
     i32, v32 = model.rank_topk(users, k=20, precision="fp32")
     scale = float(v32.abs().max())
     assert float((val - v32).abs().max()) <= 2e-3 * scale
-    same = [(len(set(a.tolist()) & set(b.tolist())) / 20.0) for a, b in zip(idx.cpu().numpy(), i32.cpu().numpy())]
-    assert np.mean(same) > 0.97
     dense = model.rate_all_items(users)
+    # the seeded (untrained) layer outputs are almost collinear, so many items tie to within the fp16
+    # operand rounding: every returned item must score, in fp32, within that rounding of the exact k-th best
+    got = torch.gather(dense, 1, idx.long())
+    assert bool((got.min(dim=1).values >= v32[:, -1] - 2e-3 * scale).all())
     ref_idx = torch.topk(dense, 20, dim=1).indices
     assert float((ref_idx == i32.long()).float().mean()) > 0.99
