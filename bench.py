@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--eval-scorer", default="f16", choices=["f16", "bf16"],
                     help="f16: fp16-accumulator filter + exact re-score (r02); bf16: round 1's fp32-accumulator kernel")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-small-configs", action="store_true", help="skip the configs[1] / configs[2] legs")
     ap.add_argument("--train-batch", type=int, default=256, help="samples per train step (main_rec.py:20: 256)")
     ap.add_argument("--loss-bench-batch", type=int, default=1 << 20,
                     help="batch on which the loss / scatter kernels are timed alone for their rooflines")
@@ -239,6 +240,128 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- BASELINE.json configs[1] and configs[2]: small graphs, timed through the drop-in model classes --------
+def bench_small_configs(torch, dev):
+    """configs[1]: LightGCN_SPEX main_11.py rec + path multi-task step on a weibo-shaped synthetic graph
+    (6 812 users, Trust_SPEX/code/main_trust.py:41-42; items and density from epinion2's ratios, SURVEY §8d;
+    50 random trust paths of 2-5 hops per user, data_process_path.py:14-15).
+    configs[2]: NGCF_SPEX propagation (SpMM + W1/W2 layer) on a twitter-shaped synthetic graph (8 930 users,
+    main_trust.py:43-44): fused inference forward, training step (forward + BCE + backward + Adam on the
+    library's kernels), and full ranking of every user on the tcgen05 scorer at D = 128."""
+    import argparse
+
+    import numpy as np
+
+    from spex_b200.dataloader import SyntheticDataset
+    from spex_b200.optim import FusedAdam
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    rng = np.random.default_rng(2020)
+    # ---- configs[1] ----
+    from spex_b200.model_expert_s import LightGCN as LightGCNExpert
+    from spex_b200.path_data import Data
+
+    nu = 6812
+    m = int(nu * 3.9)
+    ds = SyntheticDataset(nu, m, nu * 66, seed=2020)
+    args = argparse.Namespace(recdim=64, layer=3, keepprob=0.6, A_split=0, dropout=0, a_fold=1, dataset="weibo-shaped",
+                              lr=1e-3, seed=2020, hiddenSize=64, nb_heads=3, batchSize=256, nonhybrid=False, act="relu",
+                              batch_size=256)
+    torch.manual_seed(2020)
+    model = LightGCNExpert(args, ds).to(dev)
+    paths = [[int(x) for x in rng.integers(0, nu, rng.integers(2, 6))] for _ in range(nu * 50)]
+    targets = rng.integers(0, nu, len(paths)).tolist()
+    trust = Data((paths, targets), nu, shuffle=False)
+    by_user = {}
+    for i, pth in enumerate(paths):
+        by_user.setdefault(pth[0], []).append(i)
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    B = 256
+    users = torch.from_numpy(rng.integers(0, nu, B)).to(dev)
+    items = torch.from_numpy(rng.integers(0, m, B)).to(dev)
+    labels = torch.from_numpy((rng.random(B) < 1 / 6).astype(np.float32)).to(dev)
+    n_batches = -(-(ds.trainDataSize * 6) // B)
+    tbs = max(len(paths) // n_batches, 1)
+    idx = []
+    for u in set(users.tolist()):
+        idx.extend(by_user.get(u, []))
+    idx = np.array(sorted(idx)[:tbs], dtype=int)
+
+    def step11():
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        l1, l2 = model(users=users, items=items, labels=labels, slice_indices=idx, trust_data=trust, flag=0)
+        (l1 + l2).backward()
+        opt.step()
+
+    def prop11():
+        with torch.no_grad():
+            model.computer()
+
+    ms_step = timed(step11, 5)
+    ms_prop = timed(prop11, 10)
+    nnz = int(model.device_graph().nnz)
+    out["configs[1] main_11 weibo-shaped"] = {
+        "workload": f"{nu} users x {m} items, {ds.trainDataSize} interactions (nnz(A)={nnz}), {len(paths)} trust paths, "
+                    f"batch {B} + {idx.size} paths", "train_step_ms": round(ms_step, 3),
+        "computer_forward_ms": round(ms_prop, 4), "computer_gedges_per_s": nnz * 3 / (ms_prop * 1e-3) / 1e9,
+        "note": "the path branch (GraphAttentionLayer python loops, utility2/layers.py:19-40) is host-loop bound and out "
+                "of scope as a kernel target (SURVEY §2); it dominates the step"}
+    del model, opt, trust
+    # ---- configs[2] ----
+    from spex_b200.ngcf import Model_Wrapper, build_ngcf_norm_adj
+
+    nu2 = 8930
+    m2 = int(nu2 * 3.9)
+    ds2 = SyntheticDataset(nu2, m2, nu2 * 66, seed=2021, with_test=False)
+    adj = build_ngcf_norm_adj(ds2.trainUser, ds2.trainItem, nu2, m2)
+    torch.manual_seed(2020)
+    ng = Model_Wrapper({"n_users": nu2, "n_items": m2, "norm_adj": adj}, dev).to(dev)
+    opt2 = FusedAdam(ng.parameters(), lr=1e-3)
+    bu = rng.integers(0, nu2, 1024)
+    bi = rng.integers(0, m2, 1024)
+    bl = (rng.random(1024) < 1 / 6).astype(np.float32)
+
+    def ngcf_infer():
+        ng.eval()
+        with torch.no_grad():
+            ng(None, None, None, 1)
+
+    def ngcf_train():
+        ng.train()
+        opt2.zero_grad(set_to_none=True)
+        loss = ng(bu, bi, bl, 0)
+        loss.backward()
+        opt2.step()
+
+    def ngcf_rank():
+        ng.eval()
+        ng.rank_topk(torch.arange(nu2, device=dev), k=20)
+
+    ms_inf = timed(ngcf_infer, 10)
+    ms_tr = timed(ngcf_train, 5)
+    ms_rank = timed(ngcf_rank, 3)
+    out["configs[2] NGCF twitter-shaped"] = {
+        "workload": f"{nu2} users x {m2} items, {ds2.trainDataSize} interactions, nnz(D^-1(A+I))={adj.nnz}, 1 layer, "
+                    "outputs [N, 128]", "propagation_forward_ms": round(ms_inf, 4),
+        "propagation_gedges_per_s": adj.nnz / (ms_inf * 1e-3) / 1e9, "train_step_ms_batch1024": round(ms_tr, 3),
+        "fullrank_top20_all_users_ms": round(ms_rank, 3), "fullrank_users_per_s": nu2 / (ms_rank * 1e-3),
+        "scorer_tflops_d128": 2.0 * nu2 * m2 * 128 / (ms_rank * 1e-3) / 1e12}
+    return out
 
 
 # ---- training step -------------------------------------------------------------------------------------
@@ -833,6 +956,12 @@ def run_ours(args):
                                          f"(partitioned propagation of the gradient) + row-owned Adam, exchange={args.exchange}"}}
         del tr
 
+    smallj = None
+    if rank == 0 and world == 1 and not args.no_small_configs:
+        try:
+            smallj = bench_small_configs(torch, dev)
+        except Exception as e:   # secondary legs must never cost the headline line
+            smallj = {"error": f"{type(e).__name__}: {e}"}
     launches_total = _capi.launch_count() - launches0
     ck = clocks.stop() if clocks else None
 
@@ -864,7 +993,8 @@ def run_ours(args):
                        "e0_prefetch_during_last_layer": bool(world > 1 and prefetch),
                        "numa_cpus_rank0": numa_cpus,
                        "phase_ms_max_over_ranks": phase_log},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "train_step": trainj, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "eval": evalj, "train_step": trainj, "small_configs": smallj,
+            "parity": parity,
             "output_table_hash64": out_hash,
             "gpu_launches": launches_total, "gpu_launches_per_step": launches_per_step, "clocks": ck,
         }
