@@ -801,7 +801,30 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item()) / n_e2e
+        # the copies alone (same buffers, same streams, no kernels): what the host link allows per step
+        def copies_only(n_steps):
+            for i in range(n_steps):
+                b = i & 1
+                with torch.cuda.stream(s_h2d):
+                    d_in[b].copy_(h_in, non_blocking=True)
+                with torch.cuda.stream(s_d2h):
+                    h_out[b].copy_(d_out[b], non_blocking=True)
+            main.wait_stream(s_d2h)
+            main.wait_stream(s_h2d)
+
+        copies_only(2)
+        barrier()
+        ev0.record()
+        copies_only(n_e2e)
+        ev1.record()
+        barrier()
+        tc = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ms_copy = float(tc.item()) / n_e2e
         e2e = {"value": nnz * K_LAYERS / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "copies_alone_ms_per_step": ms_copy,
+               "host_link_gbs_per_direction_whole_job": N * D * 4 / (ms_copy * 1e-3) / 1e9,
                "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,  # summed over ranks
                "ms_per_step": ms_e2e, "steps": n_e2e,
                "note": "pinned host <-> device copies of every step's table on side streams, overlapped "

@@ -405,6 +405,18 @@ int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out
                         float* mcast_Y, void* stream);
 int spex_mcast_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
                            float* mcast_Y, int32_t n_ctas, void* stream);
+/* Last layer of a row-partitioned propagation with the NEXT call's E^(0) piggy-backed on its epilogue:
+ * Z = (addend * addend_scale + A.X) * z_scale (no Y output), and the warp that finishes output row r also
+ * copies row r of pub_src (this rank's slice of the next table) to rows out_row_offset + r of every rank's
+ * table - one multimem.st to pub_mcast (NVLS), or P2P stores to the n_pub_peers tables of pub_peers_host
+ * (exactly one of the two).  The E^(0) exchange then costs what the Y rows of the other layers cost,
+ * instead of a kernel of its own (spex_b200/dist.py).  D in {32, 64, 128}. */
+int spex_spmm_csr_f32_publish(const int64_t* rowptr, const int32_t* col, const float* val,
+                              const float* X, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                              const float* addend, float addend_scale, float* Z, float z_scale,
+                              const float* pub_src, float* pub_mcast,
+                              float* const* pub_peers_host, int32_t n_pub_peers,
+                              const spex_long_plan* plan, void* stream);
 /* cudaMemcpyAsync(DeviceToDevice) on `stream`: a copy-engine transfer into an IPC-mapped peer
  * table (dst may be peer memory), used for the E^(0) all-gather so that no SM is involved. */
 int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream);

@@ -116,6 +116,14 @@ struct Epilogue {
   // two-pass rows (SPEX_PLAN_TWO_PASS): partial row of the hot pass, added before anything else
   const float* partial_in;
   int64_t n_partial;
+  // piggy-backed publish (row partition, last layer): the warp that finishes output row r also copies
+  // row r of `pub_src` (this rank's slice of the NEXT call's table) into every rank's table - one
+  // multimem.st to `pub_mcast`, or P2P stores to `pub_peer[]` - so the E^(0) exchange of the next
+  // propagation rides on the last layer's epilogue exactly like the Y rows of the other layers
+  const float* pub_src;
+  float* pub_mcast;
+  float* pub_peer[8];
+  int n_pub_peers;
 };
 
 template <int D>
@@ -142,6 +150,17 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
       z.z = (a.z * ep.addend_scale + acc.z) * ep.z_scale;
       z.w = (a.w * ep.addend_scale + acc.w) * ep.z_scale;
       *reinterpret_cast<float4*>(ep.Z + off) = z;
+    }
+    if (ep.pub_src) {
+      const float4 v = ld_stream_f4(ep.pub_src + off);
+      const int64_t poff = (row + ep.peer_row_offset) * D + lane * 4;
+      if (ep.pub_mcast) {
+        st_multimem_f4(ep.pub_mcast + poff, v);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          if (p < ep.n_pub_peers) *reinterpret_cast<float4*>(ep.pub_peer[p] + poff) = v;
+      }
     }
   }
 }
@@ -404,7 +423,7 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
     default: break;
   }
   SPEX_RETURN_IF(plan && (plan->flags & SPEX_PLAN_COL_HOTBIT), SPEX_E_BADDIM);  // D in {32,64,128} only
-  SPEX_RETURN_IF(ep.partial_in != nullptr, SPEX_E_BADDIM);                       // two-pass rows: same
+  SPEX_RETURN_IF(ep.partial_in != nullptr || ep.pub_src != nullptr, SPEX_E_BADDIM);  // two-pass rows / publish: same
   // generic path handles long rows serially (no plan needed; still deterministic)
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
@@ -527,6 +546,35 @@ extern "C" int spex_spmm_csr_f32_mcast(const int64_t* rowptr, const int32_t* col
   ep.z_scale = z_scale;
   ep.peer_row_offset = out_row_offset;
   ep.mcast = mcast_Y;
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+// Last layer of a row-partitioned propagation with the NEXT call's E^(0) piggy-backed on its epilogue
+// (see Epilogue::pub_src): Z = (addend * addend_scale + A.X) * z_scale as usual, no Y output, and row r of
+// pub_src goes to rows out_row_offset + r of every rank's table through pub_mcast (NVLS) or pub_peers.
+extern "C" int spex_spmm_csr_f32_publish(const int64_t* rowptr, const int32_t* col, const float* val,
+                                         const float* X, int64_t n_rows, int32_t D, int64_t out_row_offset,
+                                         const float* addend, float addend_scale, float* Z, float z_scale,
+                                         const float* pub_src, float* pub_mcast,
+                                         float* const* pub_peers_host, int32_t n_pub_peers,
+                                         const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(!pub_src || !aligned16(pub_src) || out_row_offset < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF((pub_mcast == nullptr) == (n_pub_peers <= 0), SPEX_E_BADARG);   // exactly one of the two ways
+  SPEX_RETURN_IF(pub_mcast && !aligned16(pub_mcast), SPEX_E_ALIGN);
+  SPEX_RETURN_IF(n_pub_peers < 0 || n_pub_peers > 8 || (n_pub_peers > 0 && !pub_peers_host), SPEX_E_BADARG);
+  Epilogue ep{};
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.peer_row_offset = out_row_offset;
+  ep.pub_src = pub_src;
+  ep.pub_mcast = pub_mcast;
+  ep.n_pub_peers = pub_mcast ? 0 : n_pub_peers;
+  for (int p = 0; p < ep.n_pub_peers; ++p) {
+    SPEX_RETURN_IF(!pub_peers_host[p] || !aligned16(pub_peers_host[p]), SPEX_E_BADARG);
+    ep.pub_peer[p] = pub_peers_host[p];
+  }
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
 }
 

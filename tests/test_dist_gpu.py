@@ -67,15 +67,17 @@ def _worker(rank, world, port, q):
             # a sweep over different tables, each announced one call ahead (published to the peers by the
             # background kernel during the previous call's last layer), then an unannounced call
             ok_ring = True
-            if prop.can_prefetch():
+            # (both ways of publishing: from the last layer's own epilogue, and from the side-stream kernel)
+            for fuse in ((True, False) if prop.can_prefetch() else ()):
+                prop.fuse_publish = fuse
                 tabs = [E[r0:r1].clone(), (E[r0:r1] * 2.0 - 0.5).clone(), (E[r0:r1] * -1.0).clone(), E[r0:r1].clone()]
                 outs = [prop.propagate(t, next_E0_local=tabs[j + 1] if j + 1 < len(tabs) else tabs[1])
                         for j, t in enumerate(tabs)]
                 stale = prop.propagate(tabs[0])           # the announced table was tabs[1]: must be ignored
                 d1 = prop.propagate(tabs[1].clone())
                 d2 = prop.propagate(tabs[2].clone())
-                ok_ring = (torch.equal(outs[0], a) and torch.equal(outs[3], a) and torch.equal(stale, a)
-                           and torch.equal(outs[1], d1) and torch.equal(outs[2], d2))
+                ok_ring = ok_ring and (torch.equal(outs[0], a) and torch.equal(outs[3], a) and torch.equal(stale, a)
+                                       and torch.equal(outs[1], d1) and torch.equal(outs[2], d2))
             prop.close()
             res[f"{mode}/{e0}"] = (bool(torch.equal(a, want[r0:r1])),
                                    bool(torch.equal(a, b) and torch.equal(a, c) and ok_ring), phases)
