@@ -417,6 +417,17 @@ int spex_spmm_csr_f32_publish(const int64_t* rowptr, const int32_t* col, const f
                               const float* pub_src, float* pub_mcast,
                               float* const* pub_peers_host, int32_t n_pub_peers,
                               const spex_long_plan* plan, void* stream);
+/* Last layer of the row-partitioned BACKWARD propagation fused with the optimiser and the next exchange
+ * (main_rec.py:35-37 + the E^(0) all-gather of the next step in ONE kernel): the warp that finishes row r of
+ * dW = (addend * addend_scale + A.X) * z_scale applies dense Adam to row r of (p, m, v) - the arithmetic of
+ * spex_adam_f32 / torch.optim.Adam - and stores the UPDATED parameter row at rows out_row_offset + r of every
+ * rank's table (pub_mcast, or the n_pub_peers tables of pub_peers_host; none: no publish).  Z may be NULL. */
+int spex_spmm_csr_f32_adam(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                           int64_t n_rows, int32_t D, int64_t out_row_offset, const float* addend,
+                           float addend_scale, float* Z, float z_scale, float* p, float* m, float* v,
+                           float lr, float beta1, float beta2, float eps, int32_t step,
+                           float* pub_mcast, float* const* pub_peers_host, int32_t n_pub_peers,
+                           const spex_long_plan* plan, void* stream);
 /* cudaMemcpyAsync(DeviceToDevice) on `stream`: a copy-engine transfer into an IPC-mapped peer
  * table (dst may be peer memory), used for the E^(0) all-gather so that no SM is involved. */
 int spex_memcpy_peer_async(void* dst, const void* src, int64_t bytes, void* stream);

@@ -87,6 +87,8 @@ SIGNATURES = {
     "spex_push_rows_f32_ex": (C.c_int, [_p, _i64, _i32, _i64, C.POINTER(_p), _i32, _i32, _p]),
     "spex_spmm_csr_f32_publish": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i64, _p, _f, _p, _f, _p, _p,
                                             C.POINTER(_p), _i32, _PLAN, _p]),
+    "spex_spmm_csr_f32_adam": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i64, _p, _f, _p, _f, _p, _p, _p, _f, _f, _f, _f,
+                                         _i32, _p, C.POINTER(_p), _i32, _PLAN, _p]),
     "spex_memcpy_peer_async": (C.c_int, [_p, _p, _i64, _p]),
     "spex_push_rows_f32": (C.c_int, [_p, _i64, _i32, _i64, C.POINTER(_p), _i32, _p]),
     "spex_spmm_csr_f32_push": (

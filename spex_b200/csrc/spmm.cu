@@ -18,6 +18,7 @@
 //   * epilogue: Y = acc (next layer's input) and/or Z = (addend*a + acc)*b (running layer mean
 //     forward, g + A^T G backward).  The last layer writes only Z.
 #include "common.cuh"
+#include <math.h>
 
 namespace spex {
 
@@ -124,7 +125,21 @@ struct Epilogue {
   float* pub_mcast;
   float* pub_peer[8];
   int n_pub_peers;
+  // fused optimiser (row partition, last layer of the BACKWARD propagation): Z of this row is the row's
+  // gradient; the same warp applies dense Adam to the row of (adam_p, adam_m, adam_v) - torch.optim.Adam
+  // arithmetic, identical to spex_adam_f32 - and publishes the UPDATED parameter row instead of pub_src
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  float adam_b1, adam_b2, adam_eps, adam_step_size, adam_bc2_sqrt;
 };
+
+__device__ __forceinline__ void adam_update(float& pp, float gg, float& mm, float& vv, const Epilogue& ep) {
+  mm = mm + (gg - mm) * (1.f - ep.adam_b1);               // exp_avg.lerp_(grad, 1-beta1)
+  vv = vv * ep.adam_b2 + (1.f - ep.adam_b2) * gg * gg;    // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+  const float denom = sqrtf(vv) / ep.adam_bc2_sqrt + ep.adam_eps;
+  pp = pp - ep.adam_step_size * (mm / denom);             // param.addcdiv_(exp_avg, denom, -step_size)
+}
 
 template <int D>
 __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int64_t row, int lane) {
@@ -141,18 +156,30 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
       for (int p = 0; p < 8; ++p)
         if (p < ep.n_peers) *reinterpret_cast<float4*>(ep.peer[p] + poff) = acc;
     }
-    if (ep.Z) {
+    float4 z = acc;
+    if (ep.Z || ep.adam_p) {
       float4 a = f4_zero();
       if (ep.addend) a = ld_f4(ep.addend + off);
-      float4 z;
       z.x = (a.x * ep.addend_scale + acc.x) * ep.z_scale;
       z.y = (a.y * ep.addend_scale + acc.y) * ep.z_scale;
       z.z = (a.z * ep.addend_scale + acc.z) * ep.z_scale;
       z.w = (a.w * ep.addend_scale + acc.w) * ep.z_scale;
-      *reinterpret_cast<float4*>(ep.Z + off) = z;
+      if (ep.Z) *reinterpret_cast<float4*>(ep.Z + off) = z;
     }
-    if (ep.pub_src) {
-      const float4 v = ld_stream_f4(ep.pub_src + off);
+    float4 pnew = f4_zero();
+    if (ep.adam_p) {
+      pnew = ld_f4(ep.adam_p + off);
+      float4 mm = ld_f4(ep.adam_m + off), vv = ld_f4(ep.adam_v + off);
+      adam_update(pnew.x, z.x, mm.x, vv.x, ep);
+      adam_update(pnew.y, z.y, mm.y, vv.y, ep);
+      adam_update(pnew.z, z.z, mm.z, vv.z, ep);
+      adam_update(pnew.w, z.w, mm.w, vv.w, ep);
+      *reinterpret_cast<float4*>(ep.adam_p + off) = pnew;
+      *reinterpret_cast<float4*>(ep.adam_m + off) = mm;
+      *reinterpret_cast<float4*>(ep.adam_v + off) = vv;
+    }
+    if (ep.pub_src || (ep.adam_p && (ep.pub_mcast || ep.n_pub_peers > 0))) {
+      const float4 v = ep.adam_p ? pnew : ld_stream_f4(ep.pub_src + off);
       const int64_t poff = (row + ep.peer_row_offset) * D + lane * 4;
       if (ep.pub_mcast) {
         st_multimem_f4(ep.pub_mcast + poff, v);
@@ -423,7 +450,7 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
     default: break;
   }
   SPEX_RETURN_IF(plan && (plan->flags & SPEX_PLAN_COL_HOTBIT), SPEX_E_BADDIM);  // D in {32,64,128} only
-  SPEX_RETURN_IF(ep.partial_in != nullptr || ep.pub_src != nullptr, SPEX_E_BADDIM);  // two-pass rows / publish: same
+  SPEX_RETURN_IF(ep.partial_in != nullptr || ep.pub_src != nullptr || ep.adam_p != nullptr, SPEX_E_BADDIM);  // same
   // generic path handles long rows serially (no plan needed; still deterministic)
   const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
@@ -575,6 +602,45 @@ extern "C" int spex_spmm_csr_f32_publish(const int64_t* rowptr, const int32_t* c
     SPEX_RETURN_IF(!pub_peers_host[p] || !aligned16(pub_peers_host[p]), SPEX_E_BADARG);
     ep.pub_peer[p] = pub_peers_host[p];
   }
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+// Last layer of the row-partitioned BACKWARD propagation fused with the optimiser and the next exchange:
+// the warp that finishes row r of  dW = (addend * addend_scale + A.X) * z_scale  applies dense Adam to row r of
+// (p, m, v) (spex_adam_f32 arithmetic) and stores the updated parameter row into every rank's table (NVLS
+// multicast or P2P peers; both NULL/0: no publish).  dW itself is written only if Z != NULL.
+extern "C" int spex_spmm_csr_f32_adam(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
+                                      int64_t n_rows, int32_t D, int64_t out_row_offset, const float* addend,
+                                      float addend_scale, float* Z, float z_scale, float* p, float* m, float* v,
+                                      float lr, float beta1, float beta2, float eps, int32_t step,
+                                      float* pub_mcast, float* const* pub_peers_host, int32_t n_pub_peers,
+                                      const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(!p || !m || !v || step < 1 || out_row_offset < 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(!aligned16(p) || !aligned16(m) || !aligned16(v) || (pub_mcast && !aligned16(pub_mcast)), SPEX_E_ALIGN);
+  SPEX_RETURN_IF(pub_mcast && n_pub_peers > 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_pub_peers < 0 || n_pub_peers > 8 || (n_pub_peers > 0 && !pub_peers_host), SPEX_E_BADARG);
+  Epilogue ep{};
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.peer_row_offset = out_row_offset;
+  ep.pub_mcast = pub_mcast;
+  ep.n_pub_peers = pub_mcast ? 0 : n_pub_peers;
+  for (int q = 0; q < ep.n_pub_peers; ++q) {
+    SPEX_RETURN_IF(!pub_peers_host[q] || !aligned16(pub_peers_host[q]), SPEX_E_BADARG);
+    ep.pub_peer[q] = pub_peers_host[q];
+  }
+  ep.adam_p = p;
+  ep.adam_m = m;
+  ep.adam_v = v;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  ep.adam_b1 = beta1;
+  ep.adam_b2 = beta2;
+  ep.adam_eps = eps;
+  ep.adam_step_size = (float)((double)lr / bc1);
+  ep.adam_bc2_sqrt = (float)sqrt(bc2);
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
 }
 

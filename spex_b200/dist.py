@@ -226,6 +226,19 @@ class PartitionedPropagator:
              self.g.n_rows, self.D, self.r0, self._peer_ptrs[push_buf], self.world,
              ptr(addend), 1.0, ptr(Z_local), float(z_scale), self.g.plan(self.D), stream_ptr())
 
+    def _layer_adam(self, X_full, addend, z_scale, adam, slot):
+        """Last layer of the backward propagation + dense Adam on the owned rows + publish of the updated
+        rows into ring slot `slot` of every rank (spex_spmm_csr_f32_adam)."""
+        from ._capi import call, ptr, stream_ptr
+
+        mc = C.c_void_p(self._mc[slot]) if self.mode == "mcast" else None
+        peers = None if self.mode == "mcast" else self._peer_ptrs[slot]
+        call("spex_spmm_csr_f32_adam", ptr(self.g.rowptr), ptr(self.g.col), ptr(self.g.val), ptr(X_full),
+             self.g.n_rows, self.D, self.r0, ptr(addend), 1.0, None, float(z_scale), ptr(adam["p"]), ptr(adam["m"]),
+             ptr(adam["v"]), float(adam["lr"]), float(adam["beta1"]), float(adam["beta2"]), float(adam["eps"]),
+             int(adam["step"]), mc, peers, 0 if self.mode == "mcast" else self.world, self.g.plan(self.D),
+             stream_ptr())
+
     def _mark(self, name):
         if self.timing is not None:
             ev = torch.cuda.Event(enable_timing=True)
@@ -294,12 +307,19 @@ class PartitionedPropagator:
                (self.mode == "push" and self.e0_exchange == "push")
 
     def propagate(self, E0_local: torch.Tensor, out: torch.Tensor = None,
-                  next_E0_local: torch.Tensor = None, next_ready=None) -> torch.Tensor:
+                  next_E0_local: torch.Tensor = None, next_ready=None, first_full: torch.Tensor = None,
+                  adam: dict = None) -> torch.Tensor:
         """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]
         (written into `out` if given).  `next_E0_local`: this rank's rows of the table of the NEXT
         call, if the caller already has it (an inference / evaluation sweep over many tables, or
         the optimiser's output): it is published to all ranks while the last layer of this call runs
-        (`next_ready`: CUDA event after which next_E0_local may be read, e.g. the end of its upload)."""
+        (`next_ready`: CUDA event after which next_E0_local may be read, e.g. the end of its upload).
+        `first_full` (fused modes): a full [N, D] table every rank has already assembled locally, whose rows
+        [r0, r1) are E0_local - the first layer reads it instead of an exchange (the gradient table of the
+        training step: zero but for the batch's rows, which every rank can compute).
+        `adam` (fused modes): {p, m, v, lr, beta1, beta2, eps, step} - the result is not returned but consumed
+        as the gradient of `p` by a dense Adam fused into the last layer's epilogue, and the updated rows of
+        `p` are published as the next call's table (spex_spmm_csr_f32_adam)."""
         K = self.K
         if out is None:
             out = torch.empty_like(E0_local)
@@ -317,17 +337,30 @@ class PartitionedPropagator:
         if staged is not None and staged[1] is not None:
             torch.cuda.current_stream().wait_event(staged[1])   # the publish of the last call (even a stale one
                                                                 # must be over before this slot is written again)
-        if staged is None or staged[0] != self._key(E0_local):
+        if first_full is not None:
+            if not fused:
+                raise ValueError("first_full needs a fused exchange mode")
+        elif staged is None or staged[0] != self._key(E0_local):
             self._exchange_e0(E0_local, slot=a)
         self._mark("e0_exchange")
-        if fused:
+        if fused and first_full is None:
             self._stream_barrier()  # E^(0) complete everywhere
         self._mark("barrier")
         Y = None
         for k in range(K):
             last = k == K - 1
-            X_full = self._X[(a + k) % nt]
+            X_full = self._X[(a + k) % nt] if (k > 0 or first_full is None) else first_full
             addend = E0_local if k == 0 else out
+            if last and adam is not None:
+                if not fused:
+                    raise ValueError("the fused Adam epilogue needs a fused exchange mode")
+                self._layer_adam(X_full, addend, inv, adam, (a + K) % nt)
+                self._mark(f"layer{k + 1}")
+                done = torch.cuda.Event()
+                done.record()
+                self._staged = (self._key(adam["p"]), done)
+                self._slot = (a + K) % nt
+                return None
             publish = None
             if last and next_E0_local is not None and self.can_prefetch():
                 if fused and self.fuse_publish and self.D in (32, 64, 128) and next_E0_local.is_contiguous():
@@ -401,6 +434,11 @@ class PartitionedPropagator:
 #             (sum-of-powers instead of the single-GPU kernel's Horner form: <= 1e-6 relative, not
 #             bit-equal).  Edge dropout (non-symmetric values) is not supported in this mode.
 #   optimiser row-owned dense Adam (spex_adam_f32 on the local slice): no collective.
+# With a fused exchange (push / mcast) the tail of the step is ONE kernel per rank: the last backward layer
+# applies Adam to each owned row in its epilogue and stores the updated row into every rank's table
+# (spex_spmm_csr_f32_adam), so the next forward starts without an E^(0) exchange; and the first backward
+# layer reads a gradient table every rank assembles locally (all batch rows are known everywhere): of the
+# four exchanges of round-partitioned step only the per-layer ones remain.
 # ---------------------------------------------------------------------------------------------------
 class _CudaTrainOps:
     """The CUDA entry points behind PartitionedTrainer (no fallback: CPU tensors are rejected)."""
@@ -482,14 +520,21 @@ class PartitionedTrainer:
     of its gradient and of the Adam moments.  `prop` is the PartitionedPropagator of the same partition."""
 
     def __init__(self, prop: PartitionedPropagator, W_local: torch.Tensor, n_user_rows: int, lr: float = 1e-3,
-                 betas=(0.9, 0.999), eps: float = 1e-8, train_ops=None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, train_ops=None, fused_tail: bool = True):
         self.prop = prop
         self.W = W_local
         self.nur = int(n_user_rows)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.m = torch.zeros_like(W_local)
         self.v = torch.zeros_like(W_local)
-        self.g = torch.zeros_like(W_local)        # dL/d(out), zero except the batch's owned rows
+        # fused path (push / mcast exchange on GPUs, K >= 1, D with a vector kernel): see step()
+        self.fused = (train_ops is None and prop.mode in ("push", "mcast") and prop.K >= 1
+                      and prop.D in (32, 64, 128) and fused_tail)
+        if self.fused:
+            self.G_full = torch.zeros(prop.N, W_local.shape[1], dtype=W_local.dtype, device=W_local.device)
+            self.g = None
+        else:
+            self.g = torch.zeros_like(W_local)    # dL/d(out), zero except the batch's owned rows
         self.dW = torch.empty_like(W_local)
         self.out = torch.empty_like(W_local)
         self._dirty = None
@@ -506,6 +551,22 @@ class PartitionedTrainer:
             dist.all_reduce(R, group=p.group)
         Ru, Ri = R[:B], R[B:]
         loss, dgamma = self.ops.bce(Ru, Ri, labels.to(torch.float32))
+        self.t += 1
+        if self.fused:
+            # Every rank holds all rows of the batch, so every rank can write ALL gradient rows into its own
+            # full-size gradient table (zero elsewhere: zero-filled once, the touched rows cleared per step):
+            # the first backward layer needs no exchange.  The last one applies Adam to the owned rows in its
+            # epilogue and publishes the updated rows as the next forward's table (one kernel for
+            # main_rec.py:35-37's backward tail, the optimiser and the next all-gather).
+            if self._dirty is not None:
+                self.ops.clear_rows(self.G_full, self._dirty)
+            self.ops.scatter(rows[:B], Ri, dgamma, self.G_full, 0, 0)
+            self.ops.scatter(rows[B:], Ru, dgamma, self.G_full, 0, 0)
+            self._dirty = rows
+            p.propagate(self.G_full[r0:r1], out=self.dW, first_full=self.G_full,
+                        adam={"p": self.W, "m": self.m, "v": self.v, "lr": self.lr, "beta1": self.betas[0],
+                              "beta2": self.betas[1], "eps": self.eps, "step": self.t})
+            return loss
         if self._dirty is not None:
             self.ops.clear_rows(self.g, self._dirty)
         self.ops.scatter(rows[:B], Ri, dgamma, self.g, r0, r1)      # gU[users] = sum dgamma * I[items]
@@ -513,7 +574,6 @@ class PartitionedTrainer:
         own = (rows >= r0) & (rows < r1)
         self._dirty = (rows[own] - r0).contiguous()
         dW = p.propagate(self.g, out=self.dW)                        # (1/(K+1)) sum_k A^k g
-        self.t += 1
         self.ops.adam(self.W, dW, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps, self.t)
         return loss
 
