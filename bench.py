@@ -74,6 +74,37 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def profile_traffic(names):
+    """DRAM bytes (read + write) of the kernels whose name contains one of `names`, summed, from the newest
+    ncu summary under profiles/ that lists them all (profiles/ncu_summary.py output); (None, None) if there is
+    none.  The bench line reports it as profile-derived, with the file name, never as measured by this run."""
+    import glob
+    import re
+
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.json")), reverse=True):
+        try:
+            rows = json.load(open(path))
+        except Exception:
+            continue
+        tot, seen = 0.0, set()
+        for r in rows:
+            kn = r.get("Kernel Name", "")
+            hit = next((n for n in names if n in kn), None)
+            if hit is None or hit in seen:
+                continue
+            try:
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = r[key].split()
+                    tot += float(v) * unit[u]
+            except Exception:
+                break
+            seen.add(hit)
+        if len(seen) == len(names):
+            return tot, os.path.relpath(path, ROOT)
+    return None, None
+
+
 def workload(scale):
     return (max(int(G_USERS * scale), 1000), max(int(G_ITEMS * scale), 500),
             max(int(G_INTER * scale), 10000))
@@ -712,14 +743,16 @@ def run_ours(args):
     alg_bytes = (local_nnz + local_rows) * (8 + 4 * D)
     t_launch = ms_step * 1e-3 / K_LAYERS
     achieved = alg_bytes / t_launch / 1e9
-    # DRAM traffic per layer from the round's `ncu --set full` capture of this exact workload
-    # (profiles/r01_ncu_spmm_final.json: rows 164.73+7.58, segments 121.50+0.53, fix 0.60+0.02 GB):
-    # 295.0 GB, i.e. 0.55 of the algorithmic bytes - L2 re-use of popular item rows, no re-reads.
-    traffic = 294.96e9 if (world == 1 and args.scale == 1.0) else None
+    # DRAM traffic per layer: NOT measured by this run - read from the newest committed `ncu --set full` summary
+    # of this exact workload (full scale, one GPU) under profiles/, and labelled with its file name
+    traffic, traffic_src = (None, None)
+    if world == 1 and args.scale == 1.0:
+        traffic, traffic_src = profile_traffic(["spmm_rows_kernel<64", "spmm_seg_list_kernel<64", "spmm_long_fix_list_kernel<64"])
     roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8,1> + spmm_seg_list_kernel<64,8,1> + "
                                           "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
                 # frac > 1 is possible: the algorithmic bytes assume no cache reuse, L2 serves part of
                 # the gathers.  The DRAM-side view of the same launch: measured traffic / time / peak.
                 "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,

@@ -147,6 +147,19 @@ def main():
     G["test_users"] = np.array(sub)
     G["test_recall"], G["test_ndcg"] = np.asarray(ret["recall"]), np.asarray(ret["ndcg"])
     np.savez_compressed(os.path.join(HERE, "epinion2_golden.npz"), **G)
+    if os.environ.get("SPEX_EP2_FULL"):
+        # second fixture (epinion2_full.npz): EVERY row of computer() and of both gradients through two
+        # float64 numbers per row (sum and sum of squares), and the reference's Test() over ALL test users
+        # (one propagation per user in the reference: ~10 minutes on 8 CPU threads)
+        F = {"computer_row_sum": allrows.astype(np.float64).sum(1), "computer_row_sq": (allrows.astype(np.float64) ** 2).sum(1),
+             "grad_user_row_sum": gu.astype(np.float64).sum(1), "grad_user_row_sq": (gu.astype(np.float64) ** 2).sum(1),
+             "grad_item_row_sum": gi.astype(np.float64).sum(1), "grad_item_row_sq": (gi.astype(np.float64) ** 2).sum(1)}
+        with torch.no_grad():
+            ret_all = ref_bt.test(model, dataset.testRatings, dataset.testNegatives)
+        F["test_recall_all"], F["test_ndcg_all"] = np.asarray(ret_all["recall"]), np.asarray(ret_all["ndcg"])
+        F["n_test_users"] = len(dataset.testRatings)
+        np.savez_compressed(os.path.join(HERE, "epinion2_full.npz"), **F)
+        print("epinion2 full: test users", F["n_test_users"], "recall", F["test_recall_all"], "ndcg", F["test_ndcg_all"])
     print("epinion2: users", nu, "items", m, "train", len(dataset.trainUser), "nnz", G["adj_nnz"],
           "loss %.6f" % G["bce_loss"], "recall", G["test_recall"], "ndcg", G["test_ndcg"])
 
