@@ -134,3 +134,40 @@ def test_gpu_sampled_test_metrics_identical_on_epinion2(ep2_root, G, cuda_device
     ret = batch_test.test(model, {u: ds.testRatings[u] for u in sub}, {u: ds.testNegatives[u] for u in sub})
     assert np.array_equal(ret["recall"], G["test_recall"])
     assert np.allclose(ret["ndcg"], G["test_ndcg"], rtol=0, atol=1e-12)
+
+
+@pytest.fixture(scope="module")
+def F():
+    return dict(np.load(os.path.join(GOLD, "epinion2_full.npz")))
+
+
+@pytest.mark.gpu
+def test_gpu_every_row_and_every_test_user_on_epinion2(ep2_root, G, F, cuda_device):
+    """epinion2_full.npz (tests/golden/make_epinion2.py with SPEX_EP2_FULL=1): two float64 numbers per row
+    (sum, sum of squares) of the reference's computer() output and of both gradient tables - so EVERY row is
+    checked, not every 13th - and the reference's Test() over ALL 3 185 test users (one propagation per
+    user there, one in total here): Recall identical, NDCG to 1e-12."""
+    from spex_b200 import batch_test
+
+    ds, model = _gpu_model(ep2_root, cuda_device)
+    model.eval()
+    with torch.no_grad():
+        cu, ci = model.computer()
+    rows = torch.cat([cu, ci]).double().cpu().numpy()
+    scale = np.sqrt(F["computer_row_sq"]).max()
+    assert np.abs(rows.sum(1) - F["computer_row_sum"]).max() < 1e-5 * scale * 8          # 64 terms per row
+    assert np.abs(np.sqrt((rows ** 2).sum(1)) - np.sqrt(F["computer_row_sq"])).max() < 1e-5 * scale
+    bu, bi, bl = (torch.from_numpy(G[k]).to(cuda_device) for k in ("batch_users", "batch_items", "batch_labels"))
+    model.train()
+    model.zero_grad()
+    model(bu, bi, bl, flag=0).backward()
+    for name, grad in (("user", model.embedding_user.weight.grad), ("item", model.embedding_item.weight.grad)):
+        g = grad.double().cpu().numpy()
+        gs = np.sqrt(F[f"grad_{name}_row_sq"]).max()
+        assert np.abs(g.sum(1) - F[f"grad_{name}_row_sum"]).max() < 1e-5 * gs * 8, name
+        assert np.abs(np.sqrt((g ** 2).sum(1)) - np.sqrt(F[f"grad_{name}_row_sq"])).max() < 1e-5 * gs, name
+    model.eval()
+    assert len(ds.testRatings) == int(F["n_test_users"]) == 3185
+    ret = batch_test.test(model, ds.testRatings, ds.testNegatives)
+    assert np.array_equal(ret["recall"], F["test_recall_all"])
+    assert np.allclose(ret["ndcg"], F["test_ndcg_all"], rtol=0, atol=1e-12)
