@@ -67,8 +67,8 @@ def main():
     nw = (b_pad // 128) * 4
     out["f16"] = {"ms": round(ms, 3), "tflops": round(flops / ms / 1e9, 1), "slow_tiles_frac": st[0] / n_warp_tiles,
                   "block_calls_per_warp": st[1] / nw, "slow_path_cycles_per_warp": st[2] / nw,
-                  "compactions_per_warp": st[3] / nw, "exact_compactions_per_warp": st[4] / nw,
-                  "compaction_cycles_per_warp": st[5] / nw}
+                  "inserts_per_warp": st[3] / nw, "exact_settlements_per_warp": st[4] / nw,
+                  "exact_settlement_cycles_per_warp": st[5] / nw}
     i16 = idx.clone()
     if args.D == 64:
         Ib, m_pad2 = ops.pack_bf16(I, None, ops.TC_ITEM_MULTIPLE)
