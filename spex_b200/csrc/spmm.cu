@@ -19,6 +19,7 @@
 //     forward, g + A^T G backward).  The last layer writes only Z.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace spex {
 
@@ -99,6 +100,157 @@ __device__ __forceinline__ float4 warp_row_accumulate(const int32_t* __restrict_
 #pragma unroll
   for (int m = LPR; m < 32; m <<= 1) f4_add(acc, f4_shfl_xor(acc, m));
   return acc;
+}
+
+// ---- 256-bit gathers (the shipped path for 32-byte aligned tables) --------------------------------
+// Blackwell's LDG.256: a lane fetches 32 B, so LPR8 = D/8 lanes cover a row and one warp instruction gathers
+// G8 = 32/LPR8 neighbour rows (4 at D=64) - half the load instructions, shuffles and address arithmetic per
+// edge of the 128-bit version above.  The warp's 32-edge batch is dealt to the lane groups in CONSECUTIVE
+// runs (group g owns batch edges [g*LPR8, (g+1)*LPR8)), so that a segmented shuffle of width LPR8 with an
+// IMMEDIATE source lane hands every group its own edge: no per-lane index arithmetic.  Full batches take a
+// branch-free unrolled path, the row's last partial batch a predicated loop.  The (col, val) pair of the
+// next batch is loaded before the current batch's gathers are issued, so a row's dependent-latency chain is
+// rowptr -> col/val -> gathers, gathers, ... instead of alternating col/val and gather round trips.
+// The static L2 eviction priorities exist only on 256-bit loads (ptxas: "requires .v8.b32/.v4.b64 type with
+// .L2::evict_last"): a hot column (bit 31, kHot) selects between two predicated LDG.256 - no cache-policy
+// descriptor, no uniform-register traffic.  Summation order: fixed per row (group-local edge order, then
+// the xor tree), i.e. bit-reproducible, but different from the 128-bit kernel's.
+struct f8 {
+  float4 a, b;
+};
+__device__ __forceinline__ f8 ld_gather_f8(const float* p) {
+  f8 v;
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+      : "l"(p));
+  return v;
+}
+__device__ __forceinline__ f8 ld_gather_f8_last(const float* p) {
+  f8 v;
+  asm("ld.global.nc.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+      : "l"(p));
+  return v;
+}
+__device__ __forceinline__ f8 ld_gather_f8_first(const float* p) {
+  f8 v;
+  asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+      : "l"(p));
+  return v;
+}
+template <int D, bool kHot>
+__device__ __forceinline__ f8 gather_row8(const float* Xs, int cc) {
+  // one IMAD.WIDE.U32 (left to itself the compiler builds the 64-bit product from two shifts, two masks and
+  // a carry chain: 6 instructions per gather)
+  const float* p;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(kHot ? (uint32_t)cc & 0x7fffffffu : (uint32_t)cc), "n"(D * 4), "l"(Xs));
+  if (kHot) return cc < 0 ? ld_gather_f8_last(p) : ld_gather_f8_first(p);
+  return ld_gather_f8(p);
+}
+__device__ __forceinline__ void f8_fma(f8& acc, float s, const f8& x) {
+  f4_fma(acc.a, s, x.a);
+  f4_fma(acc.b, s, x.b);
+}
+
+// Sum over CSR edges [start, end) of val[e] * X[col[e], :]; returns, in the 128-bit kernels' layout (lane l <
+// D/4 holds floats [4l, 4l+4)), the finished row.  U = gathers in flight per lane before the first FMA.
+template <int D, int U, bool kHot>
+__device__ __forceinline__ float4 warp_row_accumulate8(const int32_t* __restrict__ col,
+                                                       const float* __restrict__ val,
+                                                       const float* __restrict__ X, int64_t start,
+                                                       int64_t end, int lane) {
+  constexpr int LPR8 = D / 8;          // lanes per row = edges per group per batch = shuffle width
+  static_assert(LPR8 % U == 0, "U must divide the group's share of a batch");
+  const int grp = lane / LPR8, sub = lane % LPR8;
+  const float* Xs = X + sub * 8;
+  f8 acc;
+  acc.a = f4_zero();
+  acc.b = f4_zero();
+  int rem = (int)(end - start);        // a row has < 2^31 edges (columns are int32 and unique)
+  const int32_t* cp = col + start + lane;
+  const float* vp = val + start + lane;
+  int c = 0;
+  float v = 0.f;
+  if (lane < rem) {
+    c = ld_stream_s32(cp);
+    v = ld_stream_f32(vp);
+  }
+  while (rem > 0) {
+    int cn = 0;
+    float vn = 0.f;
+    if (lane + 32 < rem) {             // next batch's (col, val): in flight during this batch's gathers
+      cn = ld_stream_s32(cp + 32);
+      vn = ld_stream_f32(vp + 32);
+    }
+    if (rem >= 32) {
+#pragma unroll
+      for (int k0 = 0; k0 < LPR8; k0 += U) {
+        f8 x[U];
+        float vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cc = __shfl_sync(kFull, c, k0 + u, LPR8);
+          vv[u] = __shfl_sync(kFull, v, k0 + u, LPR8);
+          x[u] = gather_row8<D, kHot>(Xs, cc);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) f8_fma(acc, vv[u], x[u]);
+      }
+    } else {
+      const int ng = rem - grp * LPR8;              // edges of this group (<= 0: none)
+      const int nmax = rem < LPR8 ? rem : LPR8;     // group 0 holds the most
+#pragma unroll 1
+      for (int k0 = 0; k0 < nmax; k0 += U) {
+        f8 x[U];
+        float vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cc = __shfl_sync(kFull, c, k0 + u, LPR8);
+          vv[u] = __shfl_sync(kFull, v, k0 + u, LPR8);
+          if (k0 + u < ng) {
+            x[u] = gather_row8<D, kHot>(Xs, cc);
+          } else {
+            x[u].a = f4_zero();
+            x[u].b = f4_zero();
+            vv[u] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) f8_fma(acc, vv[u], x[u]);
+      }
+    }
+    c = cn;
+    v = vn;
+    cp += 32;
+    vp += 32;
+    rem -= 32;
+  }
+#pragma unroll
+  for (int m = LPR8; m < 32; m <<= 1) {
+    f4_add(acc.a, f4_shfl_xor(acc.a, m));
+    f4_add(acc.b, f4_shfl_xor(acc.b, m));
+  }
+  // lane l of the 128-bit layout takes half (l & 1) of lane l / 2
+  const int src = (lane >> 1) & (LPR8 - 1);
+  float4 lo, hi;
+  lo.x = __shfl_sync(kFull, acc.a.x, src);
+  lo.y = __shfl_sync(kFull, acc.a.y, src);
+  lo.z = __shfl_sync(kFull, acc.a.z, src);
+  lo.w = __shfl_sync(kFull, acc.a.w, src);
+  hi.x = __shfl_sync(kFull, acc.b.x, src);
+  hi.y = __shfl_sync(kFull, acc.b.y, src);
+  hi.z = __shfl_sync(kFull, acc.b.z, src);
+  hi.w = __shfl_sync(kFull, acc.b.w, src);
+  return (lane & 1) ? hi : lo;
+}
+
+// kV8: 256-bit gathers (table 32-byte aligned), else the 128-bit version
+template <int D, int U, bool kHot, bool kV8>
+__device__ __forceinline__ float4 row_sum(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                          const float* __restrict__ X, int64_t start, int64_t end, int lane) {
+  if (kV8) return warp_row_accumulate8<D, (D >= 64 ? 4 : D / 8), kHot>(col, val, X, start, end, lane);
+  return warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
 }
 
 struct Epilogue {
@@ -204,8 +356,8 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
 // backfill every slot (32 CTAs = 32 warps per SM at 63 registers).
 constexpr int kRowsPerCta = SPEX_ROWS_PER_CTA;  // warps (= rows) per CTA
 
-template <int D, int U, bool kHot>
-__global__ void __launch_bounds__(kRowsPerCta * 32)
+template <int D, int U, bool kHot, bool kV8>
+__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
                  int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass,
@@ -225,13 +377,13 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
   // two-pass rows: pass 1 = hot edges [start, rowmid), pass 2 = cold edges [rowmid, end)
   if (pass == 1) end = rowmid[row];
   if (pass == 2) start = rowmid[row];
-  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
+  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, end, lane);
   row_epilogue<D>(ep, acc, row, lane);
 }
 
 // warp per segment of a long row -> partial[seg, :]
-template <int D, int U, bool kHot>
-__global__ void __launch_bounds__(kRowsPerCta * 32)
+template <int D, int U, bool kHot, bool kV8>
+__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
 spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ X,
                      const int32_t* __restrict__ long_rows,
@@ -252,7 +404,7 @@ spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restri
   const int64_t rs = rowptr[row], re = rowptr[row + 1];
   const int64_t start = rs + (int64_t)k * seg_len;
   const int64_t end = (start + seg_len < re) ? start + seg_len : re;
-  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
+  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, end, lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -276,8 +428,8 @@ spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
 // block-major order: at any moment the resident warps gather from one ~32 MB window of the
 // table, which the 126 MB L2 keeps resident, so each table row of the window comes from HBM once
 // instead of once per edge.  warp per (row, column block) segment -> partial[seg, :]
-template <int D, int U, bool kHot>
-__global__ void __launch_bounds__(kRowsPerCta * 32)
+template <int D, int U, bool kHot, bool kV8>
+__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
 spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
                      const float* __restrict__ X, const int64_t* __restrict__ seg_start,
                      const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial) {
@@ -286,7 +438,7 @@ spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ 
   const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   const int64_t start = seg_start[seg];
-  const float4 acc = warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, start + seg_count[seg], lane);
+  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, start + seg_count[seg], lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -364,7 +516,7 @@ spmm_rows_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
 
 static bool g_rows_only = false;   // spex_debug_spmm_rows: launch the short-row kernel alone
 
-template <int D, int U, bool kHot>
+template <int D, int U, bool kHot, bool kV8>
 static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                         int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
                         cudaStream_t st) {
@@ -382,18 +534,18 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
     epA.Y = plan->hot_partial;
     const int64_t gridA = (nA + kRowsPerCta - 1) / kRowsPerCta;
     if (gridA > 0) {
-      spmm_rows_kernel<D, U, kHot><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
+      spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
           rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0);
       count_launch();
     }
     Epilogue epB = ep;
     epB.partial_in = plan->hot_partial;
     epB.n_partial = nA;
-    spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+    spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
         rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split);
     count_launch();
   } else {
-    spmm_rows_kernel<D, U, kHot><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+    spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
         rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep, nullptr, 0, split);
     count_launch();
   }
@@ -402,12 +554,12 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
     const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
     const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;
     if (plan->seg_start) {   // explicit segment list (column-blocked hubs + fixed-length rest)
-      spmm_seg_list_kernel<D, U, kHot><<<gs, kRowsPerCta * 32, 0, st>>>(
+      spmm_seg_list_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
           col, val, X, plan->seg_start, plan->seg_count, plan->n_seg, plan->partial);
       spmm_long_fix_list_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
           plan->long_rows, plan->long_segptr, plan->row_seg, plan->n_long, plan->partial, ep);
     } else {                 // fixed-length segmentation
-      spmm_long_seg_kernel<D, U, kHot><<<gs, kRowsPerCta * 32, 0, st>>>(
+      spmm_long_seg_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
           rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
           plan->seg_len, plan->partial);
       spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
@@ -422,9 +574,20 @@ template <int D, int U>
 static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                       int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
                       cudaStream_t st) {
-  if (plan && (plan->flags & SPEX_PLAN_COL_HOTBIT))
-    return launch_vec_h<D, U, true>(rowptr, col, val, X, n_rows, ep, plan, st);
-  return launch_vec_h<D, U, false>(rowptr, col, val, X, n_rows, ep, plan, st);
+  // 256-bit gathers need a 32-byte aligned table (row pitch D*4 is a multiple of 32 for these D);
+  // SPEX_SPMM_LDG128=1 forces the 128-bit kernels (A/B measurements)
+  static const bool force128 = [] {
+    const char* e = getenv("SPEX_SPMM_LDG128");
+    return e && e[0] == '1';
+  }();
+  const bool v8 = !force128 && (reinterpret_cast<uintptr_t>(X) & 31u) == 0;
+  const bool hot = plan && (plan->flags & SPEX_PLAN_COL_HOTBIT);
+  if (hot) {
+    if (v8) return launch_vec_h<D, U, true, true>(rowptr, col, val, X, n_rows, ep, plan, st);
+    return launch_vec_h<D, U, true, false>(rowptr, col, val, X, n_rows, ep, plan, st);
+  }
+  if (v8) return launch_vec_h<D, U, false, true>(rowptr, col, val, X, n_rows, ep, plan, st);
+  return launch_vec_h<D, U, false, false>(rowptr, col, val, X, n_rows, ep, plan, st);
 }
 
 int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
