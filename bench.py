@@ -748,7 +748,7 @@ def run_ours(args):
     traffic, traffic_src = (None, None)
     if world == 1 and args.scale == 1.0:
         traffic, traffic_src = profile_traffic(["spmm_rows_kernel<64", "spmm_seg_list_kernel<64", "spmm_long_fix_list_kernel<64"])
-    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8,1> + spmm_seg_list_kernel<64,8,1> + "
+    roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8,1,1> + spmm_seg_list_kernel<64,8,1,1> + "
                                           "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_src,

@@ -1,6 +1,7 @@
 """spmm_blocking_sweep.py — one propagation layer of the 1B-interaction graph against the long-row
 blocking parameters (DeviceGraph._build_plan: SPEX_L2_WINDOW_MB = table bytes per column block,
-SPEX_HUB_EPB = average edges per (row, block) from which a long row is column-blocked).
+SPEX_HUB_EPB = average edges per (row, block) from which a long row is column-blocked; an optional
+third field sets seg_len, the degree above which a row takes the long-row path).
     python profiles/microbench/spmm_blocking_sweep.py [--configs 16:64,32:32,64:16]
 """
 import argparse
@@ -33,8 +34,9 @@ def main():
     Y = torch.empty_like(X)
     ref = None
     for cfg in args.configs.split(","):
-        win, epb = cfg.split(":")
+        win, epb, *rest = cfg.split(":")
         os.environ["SPEX_L2_WINDOW_MB"], os.environ["SPEX_HUB_EPB"] = win, epb
+        g.seg_len = int(rest[0]) if rest else 1024   # long-row threshold = segment cap (third field, optional)
         g._build_plan(D)
         torch.cuda.synchronize()
 
@@ -54,7 +56,7 @@ def main():
         if ref is None:
             ref = Y.clone()
         err = float((Y - ref).abs().max())
-        print(json.dumps({"window_mb": int(win), "hub_edges_per_block": int(epb), "layer_ms": round(best, 3),
+        print(json.dumps({"window_mb": int(win), "hub_edges_per_block": int(epb), "seg_len": g.seg_len, "n_long": g.n_long, "layer_ms": round(best, 3),
                           "n_seg": g.n_seg, "n_hub": getattr(g, "n_hub", 0), "partial_mb": g.n_seg * D * 4 >> 20,
                           "max_abs_diff_vs_first": err}), flush=True)
 

@@ -166,7 +166,7 @@ class DeviceGraph:
     # -- long-row plan --------------------------------------------------------------------------
     L2_WINDOW_BYTES = 16 << 20   # table bytes per column block: a window the 126 MB L2 keeps
     MIN_CB_COLS = 1024
-    HUB_EDGES_PER_BLOCK = 64     # average edges per (row, column block) that make blocking pay
+    HUB_EDGES_PER_BLOCK = 32     # average edges per (row, column block) that make blocking pay (r02 sweep: 64 -> 52.4, 32 -> 51.3, 16 -> 51.4 ms per layer)
 
     def _build_plan(self, D: int):
         dev = self.device
