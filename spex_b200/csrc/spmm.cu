@@ -245,11 +245,20 @@ __device__ __forceinline__ float4 warp_row_accumulate8(const int32_t* __restrict
   return (lane & 1) ? hi : lo;
 }
 
+// 256-bit gathers in flight per lane before the first FMA (x 32 B x 32 lanes = bytes in flight per warp) and
+// the CTAs-per-SM floor that fixes the register budget (32 -> 64 registers).  Tuning builds: -DSPEX_V8_U=8
+// -DSPEX_V8_MINB=20 (8 KB in flight per warp, 20 warps per SM).
+#ifndef SPEX_V8_U
+#define SPEX_V8_U 4
+#endif
+#ifndef SPEX_V8_MINB
+#define SPEX_V8_MINB 32
+#endif
 // kV8: 256-bit gathers (table 32-byte aligned), else the 128-bit version
 template <int D, int U, bool kHot, bool kV8>
 __device__ __forceinline__ float4 row_sum(const int32_t* __restrict__ col, const float* __restrict__ val,
                                           const float* __restrict__ X, int64_t start, int64_t end, int lane) {
-  if (kV8) return warp_row_accumulate8<D, (D >= 64 ? 4 : D / 8), kHot>(col, val, X, start, end, lane);
+  if (kV8) return warp_row_accumulate8<D, (D >= 64 ? SPEX_V8_U : D / 8), kHot>(col, val, X, start, end, lane);
   return warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
 }
 
@@ -357,7 +366,7 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
 constexpr int kRowsPerCta = SPEX_ROWS_PER_CTA;  // warps (= rows) per CTA
 
 template <int D, int U, bool kHot, bool kV8>
-__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
+__global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
                  int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass,
@@ -383,7 +392,7 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
 
 // warp per segment of a long row -> partial[seg, :]
 template <int D, int U, bool kHot, bool kV8>
-__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
+__global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ X,
                      const int32_t* __restrict__ long_rows,
@@ -429,7 +438,7 @@ spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
 // table, which the 126 MB L2 keeps resident, so each table row of the window comes from HBM once
 // instead of once per edge.  warp per (row, column block) segment -> partial[seg, :]
 template <int D, int U, bool kHot, bool kV8>
-__global__ void __launch_bounds__(kRowsPerCta * 32, 32 / kRowsPerCta)
+__global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
                      const float* __restrict__ X, const int64_t* __restrict__ seg_start,
                      const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial) {
