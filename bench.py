@@ -430,10 +430,14 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
 
     step_no = [0]
 
-    def train_step(users, items, labels, marks=None):
+    def train_step(users, items, labels, marks=None, receptive=True):
         W.grad = None
         t0 = ev() if marks is not None else None
-        out = ops.propagate_mean(W, g, K_LAYERS)
+        # receptive=True is what spex_b200.model.LightGCN.forward does in training mode: every layer restricted
+        # to the rows the batch depends on (bit-identical loss and gradients, tests/test_gpu_receptive.py);
+        # receptive=False is the reference's literal step: computer() over all N rows (main_rec.py:34)
+        rows = torch.cat([users, items + nur]) if receptive else None
+        out = ops.propagate_mean(W, g, K_LAYERS, rows_needed=rows)
         t1 = ev() if marks is not None else None
         loss = ops.bce_loss(out, nur, users, items, labels)
         t2 = ev() if marks is not None else None
@@ -447,23 +451,40 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
         return loss
 
     users, items, labels = batch(B)
-    for _ in range(2):
-        train_step(users, items, labels)
-    torch.cuda.synchronize()
-    n_steps = 4
-    e0 = ev()
-    for _ in range(n_steps):
-        loss = train_step(users, items, labels)
-    e1 = ev()
-    torch.cuda.synchronize()
-    ms_step = e0.elapsed_time(e1) / n_steps
-    marks = []
-    train_step(users, items, labels, marks)
-    torch.cuda.synchronize()
-    t0, t1, t2, t3, t4 = marks[0]
-    phases = {"forward_propagate_ms": t0.elapsed_time(t1), "bce_forward_ms": t1.elapsed_time(t2),
+
+    def measure(receptive):
+        for _ in range(2):
+            train_step(users, items, labels, receptive=receptive)
+        torch.cuda.synchronize()
+        n_steps = 4
+        e0 = ev()
+        for _ in range(n_steps):
+            loss = train_step(users, items, labels, receptive=receptive)
+        e1 = ev()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_steps
+        marks = []
+        train_step(users, items, labels, marks, receptive=receptive)
+        torch.cuda.synchronize()
+        t0, t1, t2, t3, t4 = marks[0]
+        ph = {"forward_propagate_ms": t0.elapsed_time(t1), "bce_forward_ms": t1.elapsed_time(t2),
               "backward_scatter_plus_propagate_ms": t2.elapsed_time(t3), "adam_ms": t3.elapsed_time(t4)}
-    loss_val = float(loss.item())
+        return ms, ph, float(loss.item())
+
+    # both arms start from the same weights and moments, so their first timed losses are comparable
+    W0 = W.detach().clone()
+    ms_full, phases_full, loss_full = measure(False)
+    with torch.no_grad():
+        W.copy_(W0)
+        mom.zero_()
+        var.zero_()
+    step_no[0] = 0
+    ms_step, phases, loss_val = measure(True)
+    del W0
+    S_rows = torch.unique(torch.cat([users, items + nur]))
+    R = ops.receptive_rows(g, S_rows, K_LAYERS)
+    rf_rows = [None if r is None else int(r.numel()) for r in R[1:]]
+    rf_edges = [None if r is None else g.degree_sum(r) for r in R[1:]]
 
     # kernels alone, large batch, with their algorithmic bytes
     def timed(fn, reps=5):
@@ -520,10 +541,19 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
     ops.enable_persistent_workspaces(False)
     return {"metric": "lightgcn_train_step_ms", "value": ms_step, "unit": "ms", "higher_is_better": False,
             "steps_per_s": 1e3 / ms_step, "batch": B, "loss": loss_val, "phases_ms": {k: round(v, 3) for k, v in phases.items()},
+            "receptive_field": {"rows_per_layer": rf_rows, "edges_per_layer": rf_edges, "nnz": g.nnz,
+                                "note": "layers 1..K of the forward restricted to the rows the batch depends on (null = "
+                                        "all rows); the backward mirrors it; loss and gradients bit-identical to the "
+                                        "full step"},
+            "full_computer_step": {"value": ms_full, "unit": "ms", "loss": loss_full,
+                                   "phases_ms": {k: round(v, 3) for k, v in phases_full.items()},
+                                   "note": "the reference's literal step: computer() over all N rows in forward and "
+                                           "backward (main_rec.py:34-35)", "same_loss_as_receptive_path": loss_full == loss_val},
             "config": {"workload": f"main_rec.py:30-37 step on the bench graph: forward(K={K_LAYERS}) + BCE (1 positive + 5 "
                                    f"negatives per user, device sampler) + backward + dense Adam over {N} x {D}",
                        "edges_per_step": 2 * K_LAYERS * g.nnz},
-            "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * g.nnz / (ms_step * 1e-3) / 1e9,
+            # edges actually traversed per second: quoted on the FULL step (the receptive path skips edges)
+            "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * g.nnz / (ms_full * 1e-3) / 1e9,
             "kernel_rooflines": roofs, "loss_bench_batch": Bl}
 
 
@@ -615,7 +645,7 @@ def run_ours(args):
             # push 62.9 vs mcast 60.6 GEdges/s; 8 GPUs: 197.1 vs 200.9)
             args.exchange = "mcast" if (float(ok.item()) > 0 and world >= 4) else "push"
         balance_log = []
-        n_bal = 4
+        n_bal = int(os.environ.get("SPEX_BALANCE_ROUNDS", 6))   # measured rounds + 1; the block holding the user/item boundary converges last
         for it in range(n_bal):
             r0, r1 = bounds[rank], bounds[rank + 1]
             lo, hi = int(rp_host[r0]), int(rp_host[r1])

@@ -104,6 +104,27 @@ int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* va
                       const spex_long_plan* plan, void* stream);
 
 /*
+ * The same layer restricted to a ROW SUBSET: only the listed rows of Y / Z are computed and written, each with
+ * exactly the value spex_spmm_csr_f32 would give it (same kernels, same summation order).
+ * Replaces nothing literal in the reference - it removes work the reference does: main_rec.py:34 calls
+ * computer() (model.py:66-97: all N rows of all K layers) for a mini-batch whose loss (model.py:115-120) reads
+ * only the batch's ~1.8 k rows of the result; layer K is needed on those rows only, layer K-1 on their
+ * neighbours, ... (the receptive field), and the backward pass has the mirrored sparsity.
+ *   rows        int32 [n_sel]       row ids (no duplicates, any order)
+ *   long_slots  int32 [n_long_sel]  for the listed rows of degree > plan->seg_len: their positions in
+ *                                   plan->long_rows; seg_ids int32 [n_seg_sel]: the ids of all their segments
+ * D in {32, 64, 128}.
+ */
+int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                           const float* X, int64_t n_rows, int32_t D,
+                           const int32_t* rows, int64_t n_sel,
+                           const int32_t* long_slots, int32_t n_long_sel,
+                           const int32_t* seg_ids, int32_t n_seg_sel,
+                           float* Y, const float* addend, float addend_scale,
+                           float* Z, float z_scale,
+                           const spex_long_plan* plan, void* stream);
+
+/*
  * K-layer propagation + layer mean:  out = (E0 + A·E0 + ... + A^K·E0) / (K+1)
  * E0 [N,D] is the concatenated user+item table (model.py:72); tmp0/tmp1 are [N,D] ping-pong
  * workspaces (K>=2 needs tmp0, K>=3 needs both).  The mean is accumulated in `out` by every

@@ -370,11 +370,13 @@ __global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
                  int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass,
-                 int64_t split) {
+                 int64_t split, const int32_t* __restrict__ row_sel) {
   const int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  if (split > 0) {
+  if (row_sel) {
+    row = row_sel[row];        // row subset (spex_spmm_csr_rows_f32): n_rows = length of the list
+  } else if (split > 0) {
     // SPEX_PLAN_INTERLEAVE: slot b -> rows of class A = [0, split) and class B = [split, n_rows)
     // taken in proportion (B gets slot b iff floor((b+1) nb / n) > floor(b nb / n)); a bijection
     const int64_t nb = n_rows - split;
@@ -397,11 +399,12 @@ spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restri
                      const float* __restrict__ val, const float* __restrict__ X,
                      const int32_t* __restrict__ long_rows,
                      const int32_t* __restrict__ long_segptr, int32_t n_long, int32_t n_seg,
-                     int32_t seg_len, float* __restrict__ partial) {
+                     int32_t seg_len, float* __restrict__ partial, const int32_t* __restrict__ seg_sel) {
   constexpr int LPR = RowShape<D>::LPR;
   const int lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
+  if (seg_sel) seg = seg_sel[seg];   // subset: n_seg = length of the list
   // largest r with long_segptr[r] <= seg
   int lo = 0, hi = n_long;
   while (hi - lo > 1) {
@@ -422,10 +425,11 @@ template <int D, int U>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
                      const int32_t* __restrict__ long_segptr, int32_t n_long,
-                     const float* __restrict__ partial, Epilogue ep) {
+                     const float* __restrict__ partial, Epilogue ep, const int32_t* __restrict__ slot_sel) {
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (r >= n_long) return;
+  if (slot_sel) r = slot_sel[r];     // subset: n_long = length of the list
   const float4 acc = warp_row_accumulate<D, U, 1>(nullptr, nullptr, partial, long_segptr[r],
                                                   long_segptr[r + 1], lane);
   row_epilogue<D>(ep, acc, (int64_t)long_rows[r], lane);
@@ -441,11 +445,13 @@ template <int D, int U, bool kHot, bool kV8>
 __global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
                      const float* __restrict__ X, const int64_t* __restrict__ seg_start,
-                     const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial) {
+                     const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial,
+                     const int32_t* __restrict__ seg_sel) {
   constexpr int LPR = RowShape<D>::LPR;
   const int lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
+  if (seg_sel) seg = seg_sel[seg];   // subset: n_seg = length of the list
   const int64_t start = seg_start[seg];
   const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, start + seg_count[seg], lane);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
@@ -456,10 +462,12 @@ template <int D, int U>
 __global__ void __launch_bounds__(kRowsPerCta * 32)
 spmm_long_fix_list_kernel(const int32_t* __restrict__ long_rows,
                           const int32_t* __restrict__ long_segptr, const int32_t* __restrict__ row_seg,
-                          int32_t n_long, const float* __restrict__ partial, Epilogue ep) {
+                          int32_t n_long, const float* __restrict__ partial, Epilogue ep,
+                          const int32_t* __restrict__ slot_sel) {
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
+  int r = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (r >= n_long) return;
+  if (slot_sel) r = slot_sel[r];     // subset: n_long = length of the list
   const float4 acc = warp_row_accumulate<D, U, 2>(row_seg, nullptr, partial, long_segptr[r],
                                                   long_segptr[r + 1], lane);
   row_epilogue<D>(ep, acc, (int64_t)long_rows[r], lane);
@@ -525,54 +533,75 @@ spmm_rows_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
 
 static bool g_rows_only = false;   // spex_debug_spmm_rows: launch the short-row kernel alone
 
+// Row subset of one layer (spex_spmm_csr_rows_f32): only the listed rows are computed.  `rows` lists them all
+// (the rows kernel skips the long ones exactly as in a full layer); the listed rows that take the long-row path
+// are given again as slots into plan->long_rows, together with the ids of their segments, so that they run
+// through the SAME segment -> partial -> fix-up sequence as in a full layer: a row's result does not depend on
+// whether the layer was restricted.
+struct RowSubset {
+  const int32_t* rows;
+  int64_t n_rows;
+  const int32_t* long_slots;
+  int32_t n_long;
+  const int32_t* seg_ids;
+  int32_t n_seg;
+};
+
 template <int D, int U, bool kHot, bool kV8>
 static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                         int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
-                        cudaStream_t st) {
+                        cudaStream_t st, const RowSubset* sub) {
   const bool rows_only = g_rows_only;
   const bool has_long = plan && plan->n_long > 0;
-  const int64_t grid = (n_rows + kRowsPerCta - 1) / kRowsPerCta;
+  const int64_t n_work = sub ? sub->n_rows : n_rows;
+  const int64_t grid = (n_work + kRowsPerCta - 1) / kRowsPerCta;
   if (grid > 0x7fffffffLL) return SPEX_E_TOOBIG;
-  const int64_t split = (plan && (plan->flags & SPEX_PLAN_INTERLEAVE) && plan->interleave_split > 0 &&
+  const int64_t split = (!sub && plan && (plan->flags & SPEX_PLAN_INTERLEAVE) && plan->interleave_split > 0 &&
                          plan->interleave_split < n_rows)
                             ? plan->interleave_split
                             : 0;
-  if (kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
+  const int32_t* row_sel = sub ? sub->rows : nullptr;
+  if (!sub && kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
     const int64_t nA = plan->n_split_rows < n_rows ? plan->n_split_rows : n_rows;
     Epilogue epA{};
     epA.Y = plan->hot_partial;
     const int64_t gridA = (nA + kRowsPerCta - 1) / kRowsPerCta;
     if (gridA > 0) {
       spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
-          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0);
+          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0, nullptr);
       count_launch();
     }
     Epilogue epB = ep;
     epB.partial_in = plan->hot_partial;
     epB.n_partial = nA;
     spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split);
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split, nullptr);
     count_launch();
-  } else {
+  } else if (grid > 0) {
     spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, ep, nullptr, 0, split);
+        rowptr, col, val, X, n_work, has_long ? plan->seg_len : 0, ep, nullptr, 0, split, row_sel);
     count_launch();
   }
   if (rows_only) return check_last();
   if (has_long) {
-    const int gs = (plan->n_seg + kRowsPerCta - 1) / kRowsPerCta;
-    const int gf = (plan->n_long + kRowsPerCta - 1) / kRowsPerCta;
+    const int32_t n_seg = sub ? sub->n_seg : plan->n_seg;
+    const int32_t n_long = sub ? sub->n_long : plan->n_long;
+    const int32_t* seg_sel = sub ? sub->seg_ids : nullptr;
+    const int32_t* slot_sel = sub ? sub->long_slots : nullptr;
+    if (n_long == 0) return check_last();
+    const int gs = (n_seg + kRowsPerCta - 1) / kRowsPerCta;
+    const int gf = (n_long + kRowsPerCta - 1) / kRowsPerCta;
     if (plan->seg_start) {   // explicit segment list (column-blocked hubs + fixed-length rest)
       spmm_seg_list_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
-          col, val, X, plan->seg_start, plan->seg_count, plan->n_seg, plan->partial);
+          col, val, X, plan->seg_start, plan->seg_count, n_seg, plan->partial, seg_sel);
       spmm_long_fix_list_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
-          plan->long_rows, plan->long_segptr, plan->row_seg, plan->n_long, plan->partial, ep);
+          plan->long_rows, plan->long_segptr, plan->row_seg, n_long, plan->partial, ep, slot_sel);
     } else {                 // fixed-length segmentation
       spmm_long_seg_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
-          rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, plan->n_seg,
-          plan->seg_len, plan->partial);
+          rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, n_seg,
+          plan->seg_len, plan->partial, seg_sel);
       spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
-          plan->long_rows, plan->long_segptr, plan->n_long, plan->partial, ep);
+          plan->long_rows, plan->long_segptr, n_long, plan->partial, ep, slot_sel);
     }
     count_launch(2);
   }
@@ -582,7 +611,7 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
 template <int D, int U>
 static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                       int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
-                      cudaStream_t st) {
+                      cudaStream_t st, const RowSubset* sub) {
   // 256-bit gathers need a 32-byte aligned table (row pitch D*4 is a multiple of 32 for these D);
   // SPEX_SPMM_LDG128=1 forces the 128-bit kernels (A/B measurements)
   static const bool force128 = [] {
@@ -592,16 +621,16 @@ static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* va
   const bool v8 = !force128 && (reinterpret_cast<uintptr_t>(X) & 31u) == 0;
   const bool hot = plan && (plan->flags & SPEX_PLAN_COL_HOTBIT);
   if (hot) {
-    if (v8) return launch_vec_h<D, U, true, true>(rowptr, col, val, X, n_rows, ep, plan, st);
-    return launch_vec_h<D, U, true, false>(rowptr, col, val, X, n_rows, ep, plan, st);
+    if (v8) return launch_vec_h<D, U, true, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+    return launch_vec_h<D, U, true, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
   }
-  if (v8) return launch_vec_h<D, U, false, true>(rowptr, col, val, X, n_rows, ep, plan, st);
-  return launch_vec_h<D, U, false, false>(rowptr, col, val, X, n_rows, ep, plan, st);
+  if (v8) return launch_vec_h<D, U, false, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+  return launch_vec_h<D, U, false, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
 }
 
 int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                 int64_t n_rows, int32_t D, const Epilogue& ep, const spex_long_plan* plan,
-                cudaStream_t st) {
+                cudaStream_t st, const RowSubset* sub = nullptr) {
   SPEX_RETURN_IF(!rowptr || !X || n_rows < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(n_rows > 0 && (!col || !val), SPEX_E_BADARG);
   SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
@@ -616,11 +645,12 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
   }
   if (n_rows == 0) return 0;
   switch (D) {
-    case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st);
-    case 64: return launch_vec<64, SPEX_U64>(rowptr, col, val, X, n_rows, ep, plan, st);
-    case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st);
+    case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+    case 64: return launch_vec<64, SPEX_U64>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+    case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
     default: break;
   }
+  SPEX_RETURN_IF(sub != nullptr, SPEX_E_BADDIM);   // row subsets: D in {32, 64, 128} only
   SPEX_RETURN_IF(plan && (plan->flags & SPEX_PLAN_COL_HOTBIT), SPEX_E_BADDIM);  // D in {32,64,128} only
   SPEX_RETURN_IF(ep.partial_in != nullptr || ep.pub_src != nullptr || ep.adam_p != nullptr, SPEX_E_BADDIM);  // same
   // generic path handles long rows serially (no plan needed; still deterministic)
@@ -708,6 +738,31 @@ extern "C" int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, cons
   ep.n_peers = 0;
   ep.peer_row_offset = 0;
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream);
+}
+
+// One layer restricted to a row subset (the receptive field of a mini-batch: LightGCN_SPEX/code/main_rec.py:34
+// calls computer() - all N rows of all K layers - for a batch of 256 users; the loss reads ~1.8 k rows of the
+// result, which need E^(K-1) only on their neighbours, and so on).  rows: int32 [n_sel] row ids, any order, no
+// duplicates; rows with degree > plan->seg_len are skipped by the rows kernel and must be given again as
+// long_slots (their positions in plan->long_rows) with seg_ids = the ids of all their segments.  Every listed
+// row gets exactly the value a full spex_spmm_csr_f32 would give it; the other rows of Y / Z are not touched.
+extern "C" int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                                      const float* X, int64_t n_rows, int32_t D, const int32_t* rows,
+                                      int64_t n_sel, const int32_t* long_slots, int32_t n_long_sel,
+                                      const int32_t* seg_ids, int32_t n_seg_sel, float* Y, const float* addend,
+                                      float addend_scale, float* Z, float z_scale, const spex_long_plan* plan,
+                                      void* stream) {
+  SPEX_RETURN_IF(n_sel < 0 || n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows), SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_long_sel > 0 && (!long_slots || !seg_ids || !plan || n_seg_sel < n_long_sel), SPEX_E_BADARG);
+  if (n_sel == 0) return 0;
+  Epilogue ep{};
+  ep.Y = Y;
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  RowSubset sub{rows, n_sel, long_slots, n_long_sel, seg_ids, n_seg_sel};
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, &sub);
 }
 
 extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,

@@ -149,14 +149,30 @@ class LightGCN(BasicModel):
         return val, valT
 
     # ---- propagation ---------------------------------------------------------------------------
-    def _propagate(self) -> torch.Tensor:
-        """[N, D] layer-mean embeddings; rows [0, n_users] users, the rest items."""
+    def _propagate(self, rows_needed=None) -> torch.Tensor:
+        """[N, D] layer-mean embeddings; rows [0, n_users] users, the rest items.  With `rows_needed`
+        (training step) only those rows of the result are valid: every layer is restricted to the rows the
+        batch depends on (ops.propagate_mean), loss and gradients unchanged bit for bit."""
         g = self.device_graph()
         table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
         val = valT = None
         if self.args_r.dropout and self.training:
             val, valT = self._dropout_values(g)
-        return ops.propagate_mean(table, g, self.n_layers, val, valT)
+        return ops.propagate_mean(table, g, self.n_layers, val, valT, rows_needed=rows_needed)
+
+    # main_rec.py:34 runs computer() over all N rows for a batch of 256: the training loss reads ~1.8 k of them.
+    # True: forward(flag=0) / bpr_loss in training mode compute only the batch's receptive field.
+    receptive_field = True
+
+    def _batch_rows(self, users, *item_lists):
+        """Row ids of the fused table a batch touches, or None when the full table is wanted."""
+        if not (self.receptive_field and self.training and torch.is_grad_enabled()
+                and type(self)._compute_final is LightGCN._compute_final and not self._freeze):
+            return None
+        dev = self.embedding_user.weight.device
+        parts = [torch.as_tensor(users, device=dev).long().reshape(-1)]
+        parts += [torch.as_tensor(i, device=dev).long().reshape(-1) + self.n_user_rows for i in item_lists]
+        return torch.cat(parts)
 
     def _compute_final(self) -> torch.Tensor:
         """The [N, D] table forward() scores against (subclasses add the expert gate)."""
@@ -197,7 +213,8 @@ class LightGCN(BasicModel):
     def forward(self, users, items, labels, flag=0):
         if flag not in (0, 1):
             raise UnboundLocalError("loss")  # the reference falls through to `return loss` unbound
-        out = self._final()
+        rows = self._batch_rows(users, items)
+        out = self._final() if rows is None else self._propagate(rows_needed=rows)
         if flag == 1:
             return ops.gather_dot(out, self.n_user_rows, users, items)
         return ops.bce_loss(out, self.n_user_rows, users, items, labels)
@@ -206,7 +223,8 @@ class LightGCN(BasicModel):
     def bpr_loss(self, users, pos, neg):
         """(loss, reg_loss): mean softplus(<u,n> - <u,p>) and 0.5*(|u0|^2+|p0|^2+|n0|^2)/B with
         u,p,n from computer() and u0,p0,n0 the raw embedding rows."""
-        out = self._final()
+        rows = self._batch_rows(users, pos, neg)
+        out = self._final() if rows is None else self._propagate(rows_needed=rows)
         table = _FusedTable.apply(self.embedding_user.weight, self.embedding_item.weight, self._table)
         return ops.bpr_loss(out, table, self.n_user_rows, users, pos, neg)
 

@@ -381,6 +381,50 @@ class DeviceGraph:
             self._plan_D = D
         return C.byref(self._plan_struct)
 
+    # -- row subsets (receptive field of a mini-batch) ----------------------------------------------
+    def _edge_positions(self, rows: torch.Tensor):
+        """Positions in col/val of all edges of `rows` (int64 ids), row by row."""
+        a = self.rowptr[rows]
+        cnt = self.rowptr[rows + 1] - a
+        total = int(cnt.sum().item())
+        first = torch.cumsum(cnt, 0) - cnt
+        pos = torch.repeat_interleave(a - first, cnt, output_size=total) + torch.arange(total, device=self.device)
+        return pos, total
+
+    def degree_sum(self, rows: torch.Tensor) -> int:
+        return int((self.rowptr[rows + 1] - self.rowptr[rows]).sum().item())
+
+    def neighbors(self, rows: torch.Tensor) -> torch.Tensor:
+        """Sorted unique column ids of the listed rows (int64): the rows a layer restricted to `rows` reads."""
+        pos, total = self._edge_positions(rows)
+        if total == 0:
+            return torch.empty(0, dtype=torch.int64, device=self.device)
+        c = self.col[pos]
+        if self.col_hot:
+            c = c & 0x7FFFFFFF
+        return torch.unique(c.to(torch.int64))
+
+    def row_subset(self, rows: torch.Tensor):
+        """(rows int32, long_slots int32 | None, seg_ids int32 | None) for spex_spmm_csr_rows_f32: the listed
+        rows, and - for those on the long-row path - their slots in the plan with all their segments."""
+        rows = rows.to(torch.int64)
+        r32 = rows.to(torch.int32).contiguous()
+        if self.n_long == 0:
+            return r32, None, None
+        deg = self.rowptr[rows + 1] - self.rowptr[rows]
+        lr = rows[deg > self.seg_len]
+        if lr.numel() == 0:
+            return r32, None, None
+        slots = torch.searchsorted(self.long_rows.to(torch.int64), lr)
+        segptr = self.long_segptr.to(torch.int64)
+        a = segptr[slots]
+        cnt = segptr[slots + 1] - a
+        total = int(cnt.sum().item())
+        first = torch.cumsum(cnt, 0) - cnt
+        pos = torch.repeat_interleave(a - first, cnt, output_size=total) + torch.arange(total, device=self.device)
+        seg_ids = self.row_seg[pos] if self.row_seg is not None else pos.to(torch.int32)
+        return r32, slots.to(torch.int32).contiguous(), seg_ids.to(torch.int32).contiguous()
+
     # -- derived graphs -------------------------------------------------------------------------
     def with_values(self, val: torch.Tensor, symmetric: bool) -> "DeviceGraph":
         g = object.__new__(DeviceGraph)
@@ -430,6 +474,107 @@ def spmm(g: DeviceGraph, X: torch.Tensor, Y: Optional[torch.Tensor] = None,
     return Y if Y is not None else Z
 
 
+def spmm_rows(g: DeviceGraph, X: torch.Tensor, subset, Y: Optional[torch.Tensor] = None,
+              addend: Optional[torch.Tensor] = None, addend_scale: float = 1.0,
+              Z: Optional[torch.Tensor] = None, z_scale: float = 1.0, val: Optional[torch.Tensor] = None):
+    """spmm() restricted to the rows of `subset` (= g.row_subset(rows)): the listed rows of Y / Z get exactly
+    the values a full layer gives them, the other rows are left untouched."""
+    _need_cuda(X)
+    X = _f32c(X)
+    D = X.shape[1]
+    if X.shape[0] != g.n_cols:
+        raise ValueError(f"X has {X.shape[0]} rows, graph has {g.n_cols} columns")
+    if Y is None and Z is None:
+        raise ValueError("spmm_rows writes into caller-provided Y and/or Z")
+    rows, slots, segs = subset
+    v = g.val if val is None else val
+    call("spex_spmm_csr_rows_f32", ptr(g.rowptr), ptr(g.col), ptr(v), ptr(X), g.n_rows, D, ptr(rows), rows.numel(),
+         ptr(slots), 0 if slots is None else slots.numel(), ptr(segs), 0 if segs is None else segs.numel(),
+         ptr(Y), ptr(addend), float(addend_scale), ptr(Z), float(z_scale), g.plan(D), stream_ptr())
+
+
+# A layer is restricted to a row list only while the list's edges stay below SUBSET_MAX_EDGE_FRAC of nnz(A)
+# (beyond it the skipped rows no longer pay for the indirection), and a list is expanded to its neighbour set
+# only while it has fewer than EXPAND_MAX_EDGE_FRAC * nnz(A) edges (the set is built by a gather + sort).
+SUBSET_MAX_EDGE_FRAC = 0.5
+EXPAND_MAX_EDGE_FRAC = 0.02
+
+
+def receptive_rows(graph: DeviceGraph, S: torch.Tensor, K: int):
+    """R[k], k = 1..K: the rows of E^(k) that the rows S of the layer mean depend on - R[K] = S,
+    R[k] = S + neighbours(R[k+1]) - or None = all rows, from the first set that outgrows the limits on."""
+    R = [None] * (K + 1)
+    if K < 1 or graph.degree_sum(S) > SUBSET_MAX_EDGE_FRAC * graph.nnz:
+        return R
+    R[K] = S
+    for k in range(K - 1, 0, -1):
+        if graph.degree_sum(R[k + 1]) > EXPAND_MAX_EDGE_FRAC * graph.nnz:
+            break
+        cand = torch.unique(torch.cat([S, graph.neighbors(R[k + 1])]))
+        if graph.degree_sum(cand) > SUBSET_MAX_EDGE_FRAC * graph.nnz:
+            break
+        R[k] = cand
+    return R
+
+
+class _PropagateMeanRows(torch.autograd.Function):
+    """_PropagateMean for a training step whose loss reads only the rows S of the result: every layer is
+    computed on the rows the batch depends on (receptive_rows) with the same kernels and epilogues, so the
+    rows S of `out`, the loss and dE0 are bit-identical to the full computation; the other rows of `out`
+    are NOT valid.  Backward contract: the incoming gradient is zero outside the rows S."""
+
+    @staticmethod
+    def forward(ctx, table, graph: DeviceGraph, K: int, val, valT, S):
+        _need_cuda(table)
+        E0 = _f32c(table)
+        N, D = E0.shape
+        R = receptive_rows(graph, S, K)
+        subs = [None if r is None else graph.row_subset(r) for r in R]
+        out = torch.empty_like(E0) if not workspaces.enabled else workspaces.get("prop_out", E0.shape, E0.device)[0]
+        tmp = [workspaces.get("prop_tmp0", E0.shape, E0.device)[0] if K >= 2 else None,
+               workspaces.get("prop_tmp1", E0.shape, E0.device)[0] if K >= 3 else None]
+        v = graph.val if val is None else val
+        inv = 1.0 / float(K + 1)
+        X = E0
+        for k in range(1, K + 1):
+            last = k == K
+            Y = None if last else tmp[(k - 1) & 1]
+            kw = dict(Y=Y, addend=E0 if k == 1 else out, addend_scale=1.0, Z=out, z_scale=inv if last else 1.0, val=v)
+            if subs[k] is None:
+                spmm(graph, X, **kw)
+            else:
+                spmm_rows(graph, X, subs[k], **kw)
+            X = Y
+        ctx.graph, ctx.K, ctx.valT, ctx.subs, ctx.R = graph, K, (v if valT is None else valT), subs, R
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        graph, K, subs, R = ctx.graph, ctx.K, ctx.subs, ctx.R
+        g = _f32c(g)
+        N, D = g.shape
+        dE0 = torch.empty_like(g) if not workspaces.enabled else workspaces.get("prop_dE0", g.shape, g.device)[0]
+        tmp = [workspaces.get("prop_tmp0", g.shape, g.device)[0] if K >= 2 else None,
+               workspaces.get("prop_tmp1", g.shape, g.device)[0] if K >= 3 else None]
+        inv = 1.0 / float(K + 1)
+        # H_0 = g; H_j = g + A^T H_{j-1}, non-zero only on R[K - j]: a restricted layer writes its rows into a
+        # zero table (zero-filled once; afterwards only the rows of the previous step are cleared)
+        X = g
+        for j in range(1, K + 1):
+            last = j == K
+            sub = subs[K - j] if j < K else None
+            kw = dict(addend=g, addend_scale=1.0, z_scale=inv if last else 1.0, val=ctx.valT)
+            if sub is None:
+                Z = dE0 if last else tmp[(j - 1) & 1]
+                spmm(graph, X, Z=Z, **kw)
+            else:
+                Z, zkey = workspaces.get(f"prop_bwd_rows{j}", g.shape, g.device, zero=True)
+                spmm_rows(graph, X, sub, Z=Z, **kw)
+                workspaces.mark(zkey, R[K - j])
+            X = Z
+        return dE0, None, None, None, None, None
+
+
 class _PropagateMean(torch.autograd.Function):
     """out = mean_k A^k E0 over the fused [N, D] table (model.py:66-97), backward through A^T."""
 
@@ -461,11 +606,17 @@ class _PropagateMean(torch.autograd.Function):
 
 
 def propagate_mean(table: torch.Tensor, graph: DeviceGraph, K: int,
-                   val: Optional[torch.Tensor] = None, valT: Optional[torch.Tensor] = None):
+                   val: Optional[torch.Tensor] = None, valT: Optional[torch.Tensor] = None,
+                   rows_needed: Optional[torch.Tensor] = None):
     """K-layer propagation + layer mean.  `val` overrides the graph values (edge dropout); the
-    backward then needs `valT` (values of the transposed matrix) unless the override is symmetric."""
+    backward then needs `valT` (values of the transposed matrix) unless the override is symmetric.
+    `rows_needed` (int64 row ids): the caller reads - and back-propagates into - only these rows of the
+    result; the layers are then restricted to the rows they depend on (_PropagateMeanRows)."""
     if graph.n_rows != graph.n_cols or table.shape[0] != graph.n_rows:
         raise ValueError("propagate_mean needs the full square adjacency and an [N, D] table")
+    if rows_needed is not None and int(K) >= 1 and table.shape[1] in (32, 64, 128):
+        S = torch.unique(_i64c(rows_needed, table.device))
+        return _PropagateMeanRows.apply(table, graph, int(K), val, valT, S)
     return _PropagateMean.apply(table, graph, int(K), val, valT)
 
 
