@@ -855,7 +855,7 @@ def run_ours(args):
 
         e2e_run(2)
         barrier()
-        n_e2e = max(10, args.steps)   # enough steps to amortise the pipeline fill (first upload) and drain (last download)
+        n_e2e = max(20, args.steps)   # enough steps to amortise the pipeline fill (first upload) and drain (last download)
         ev0.record()
         e2e_run(n_e2e)
         ev1.record()

@@ -166,7 +166,7 @@ class DeviceGraph:
     # -- long-row plan --------------------------------------------------------------------------
     L2_WINDOW_BYTES = 16 << 20   # table bytes per column block: a window the 126 MB L2 keeps
     MIN_CB_COLS = 1024
-    HUB_EDGES_PER_BLOCK = 32     # average edges per (row, column block) that make blocking pay (r02 sweep: 64 -> 52.4, 32 -> 51.3, 16 -> 51.4 ms per layer)
+    HUB_EDGES_PER_BLOCK = 16     # average edges per (row, column block) that make blocking pay (r02 sweep, ms per layer / GB of DRAM reads of the segment kernel: 64 -> 52.4 / 118, 32 -> 51.3 / 98, 16 -> 51.4 / 84)
 
     def _build_plan(self, D: int):
         dev = self.device
@@ -267,7 +267,9 @@ class DeviceGraph:
         """
         if self.col_hot:
             return -1
-        budget = self.HOT_L2_BYTES if budget_bytes is None else budget_bytes
+        import os as _os
+        budget = budget_bytes if budget_bytes is not None else (
+            int(_os.environ.get("SPEX_HOT_L2_MB", 0)) << 20 or self.HOT_L2_BYTES)   # env: tuning sweeps
         n_hot = min(budget // (D * 4), self.n_cols)
         if self.n_cols * D * 4 <= 2 * budget or n_hot <= 0 or D not in (32, 64, 128):
             return 0  # the table fits in L2 anyway / generic-D path has no hint variant
