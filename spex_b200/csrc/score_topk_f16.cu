@@ -496,7 +496,9 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
     if (dbg & 1) thrf = INFINITY;
     // merge cursor over the row's training items (ascending CSR row of R): the next training item id
     // lives in a register, the cursor itself in shared memory (only touched when it advances)
-    int mnext = 0x7fffffff;
+    // (and the one after it in mnext2: when the cursor advances the load of the following id is issued but
+    // not waited for - a single-step advance, the common case, costs no global-memory round trip)
+    int mnext = 0x7fffffff, mnext2 = 0x7fffffff;
     {
       const int32_t* c = mask_col;
       const int32_t* e = mask_col;
@@ -505,6 +507,7 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
         c = mask_col + mask_rowptr[uid];
         e = mask_col + mask_rowptr[uid + 1];
         if (c < e) mnext = __ldg(c);
+        if (c + 1 < e) mnext2 = __ldg(c + 1);
       }
       mc.cur[row] = c;
       mc.end[row] = e;
@@ -602,7 +605,8 @@ score_topk_f16_kernel(const uint8_t* __restrict__ Uh, const uint8_t* __restrict_
               const int32_t* e = mc.end[row];
               do {
                 ++c;
-                mnext = (c < e) ? __ldg(c) : 0x7fffffff;
+                mnext = mnext2;
+                mnext2 = (c + 1 < e) ? __ldg(c + 1) : 0x7fffffff;
               } while (mnext < id);
               mc.cur[row] = c;
             }
