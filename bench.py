@@ -396,14 +396,30 @@ def bench_small_configs(torch, dev):
 
 
 # ---- training step -------------------------------------------------------------------------------------
+def sample_train_batch(torch, g, nur, m, n, gen):
+    """n samples drawn like the reference (LightGCN_SPEX/code/utility1/dataloader.py:250-265): users uniform, one
+    positive per user uniform among the user's interactions (so popular items are drawn often) + 5 rejection-
+    sampled negatives (device sampler).  Needs the full adjacency `g` on the device."""
+    from spex_b200.dataloader import sample_negatives_device
+
+    dev = g.rowptr.device
+    nu = nur - 1
+    u = torch.randint(0, nu, (n // 6 + 1,), device=dev, generator=gen)
+    e = g.rowptr[u] + (torch.rand(u.numel(), device=dev, generator=gen) * (g.rowptr[u + 1] - g.rowptr[u])).long()
+    pos = (g.col[e] & 0x7FFFFFFF).long() - nur
+    neg = sample_negatives_device(g.rowptr, g.col, nur, m, u, 5, seed=int(n) + 1)
+    users = torch.cat([u, u.repeat_interleave(5)])[:n].contiguous()
+    items = torch.cat([pos, neg.reshape(-1)])[:n].contiguous()
+    labels = torch.cat([torch.ones_like(u), torch.zeros(u.numel() * 5, dtype=u.dtype, device=dev)])[:n]
+    return users, items, labels.float().contiguous()
+
+
 def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, peak_kind, dev):
     """One optimiser step of the reference loop (LightGCN_SPEX/code/main_rec.py:30-37) on the bench graph:
     computer() forward, gather + dot + BCEWithLogits, backward (deterministic scatter, K A^T SpMMs), dense
     Adam over the fused table - through the public operators, persistent workspaces on.  Per-phase CUDA
     events, and the loss / scatter / Adam / dropout-value kernels timed alone on a large batch for their
     HBM rooflines (algorithmic bytes per sample or element as in DESIGN.md §4)."""
-    from spex_b200.dataloader import sample_negatives_device
-
     ops.enable_persistent_workspaces(True)
     W = table.clone().requires_grad_(True)
     mom, var = torch.zeros_like(W), torch.zeros_like(W)
@@ -413,15 +429,7 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
     nu = nur - 1
 
     def batch(n):
-        # reference sampling (dataloader.py:250-265): one positive + 5 rejection-sampled negatives
-        u = torch.randint(0, nu, (n // 6 + 1,), device=dev, generator=gen)
-        e = g.rowptr[u] + (torch.rand(u.numel(), device=dev, generator=gen) * (g.rowptr[u + 1] - g.rowptr[u])).long()
-        pos = (g.col[e] & 0x7FFFFFFF).long() - nur
-        neg = sample_negatives_device(g.rowptr, g.col, nur, m, u, 5, seed=int(n) + 1)
-        users = torch.cat([u, u.repeat_interleave(5)])[:n].contiguous()
-        items = torch.cat([pos, neg.reshape(-1)])[:n].contiguous()
-        labels = torch.cat([torch.ones_like(u), torch.zeros(u.numel() * 5, dtype=u.dtype, device=dev)])[:n]
-        return users, items, labels.float().contiguous()
+        return sample_train_batch(torch, g, nur, m, n, gen)
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
@@ -698,6 +706,11 @@ def run_ours(args):
         lg = ops.DeviceGraph(lg.rowptr, lg.col.clone(), lg.val.clone(), N, None, g.seg_len, row_offset=r0,
                              col_hot=g.col_hot)
         E0_local = table[r0:r1].clone()
+        train_batch = None
+        if not args.no_train:   # the same sampling as at N = 1 (same seed on every rank), while the full graph is here
+            gen_t = torch.Generator(device=dev)
+            gen_t.manual_seed(11)
+            train_batch = sample_train_batch(torch, g, nur, m, args.train_batch, gen_t)
         del g, table
         torch.cuda.empty_cache()
         prop = PartitionedPropagator(lg, bounds, D, K_LAYERS, mode=args.exchange, device=dev)
@@ -1016,31 +1029,43 @@ def run_ours(args):
         # partitioned propagation applied to the gradient
         from spex_b200.dist import PartitionedTrainer
 
-        tr = PartitionedTrainer(prop, E0_local.clone(), nur, lr=1e-3)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(11)
         Bt = args.train_batch
-        tu = torch.randint(0, nu, (Bt,), device=dev, generator=gen)
-        ti = torch.randint(0, m, (Bt,), device=dev, generator=gen)
-        tl = (torch.rand(Bt, device=dev, generator=gen) < (1.0 / 6.0)).float()
-        for _ in range(2):
-            tr.step(tu, ti, tl)
-        barrier()
-        n_tr = 4
-        ev0.record()
-        for _ in range(n_tr):
-            tloss = tr.step(tu, ti, tl)
-        ev1.record()
-        barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_tr = float(t.item()) / n_tr
+        tu, ti, tl = train_batch
+        W_start = E0_local.clone()
+
+        def measure_tr(receptive):
+            tr = PartitionedTrainer(prop, W_start.clone(), nur, lr=1e-3)
+            tr.receptive_field = receptive
+            prop._staged = None        # the table of the previous arm is not this one's
+            for _ in range(2):
+                tr.step(tu, ti, tl)
+            barrier()
+            n_tr = 4
+            ev0.record()
+            for _ in range(n_tr):
+                tloss = tr.step(tu, ti, tl)
+            ev1.record()
+            barrier()
+            t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / n_tr, float(tloss.item())
+
+        ms_tr_full, loss_full = measure_tr(False)
+        ms_tr, loss_rf = measure_tr(True)
+        sets = prop.receptive_sets(torch.unique(torch.cat([tu, ti + nur])))
         trainj = {"metric": "lightgcn_train_step_ms", "value": ms_tr, "unit": "ms", "higher_is_better": False,
-                  "steps_per_s": 1e3 / ms_tr, "batch": Bt, "loss": float(tloss.item()),
-                  "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * nnz / (ms_tr * 1e-3) / 1e9,
-                  "config": {"workload": f"main_rec.py:30-37 step, row-partitioned x{world}: forward + BCE + backward "
-                                         f"(partitioned propagation of the gradient) + row-owned Adam, exchange={args.exchange}"}}
-        del tr
+                  "steps_per_s": 1e3 / ms_tr, "batch": Bt, "loss": loss_rf,
+                  "receptive_field": {"rows_per_layer": [None if r is None else int(r.numel()) for r in sets[1:]],
+                                      "note": "FORWARD layers restricted to the rows the batch depends on (null = all "
+                                              "rows), restricted rows exchanged by the same fused epilogue; the "
+                                              "backward runs all rows; loss and weights bit-identical to the full step"},
+                  "full_computer_step": {"value": ms_tr_full, "unit": "ms", "loss": loss_full,
+                                         "same_loss_as_receptive_path": loss_full == loss_rf},
+                  # edges actually traversed per second: quoted on the FULL step
+                  "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * nnz / (ms_tr_full * 1e-3) / 1e9,
+                  "config": {"workload": f"main_rec.py:30-37 step, row-partitioned x{world}: forward + BCE (1 positive + 5 "
+                                         f"negatives per user, as at N=1) + backward (partitioned propagation of the "
+                                         f"gradient) + row-owned Adam fused into the last backward layer, exchange={args.exchange}"}}
 
     smallj = None
     if rank == 0 and world == 1 and not args.no_small_configs:

@@ -426,6 +426,20 @@ int spex_mcast_rows_f32(const float* src, int64_t n_rows, int32_t D, int64_t out
                         float* mcast_Y, void* stream);
 int spex_mcast_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t out_row_offset,
                            float* mcast_Y, int32_t n_ctas, void* stream);
+/* spex_spmm_csr_rows_f32 with the fused exchange of the row-partitioned modes: the listed rows (LOCAL ids of the
+ * rank's row block) are computed and their Y rows stored at rows out_row_offset + row of every rank's next-layer
+ * table - one multimem.st per row to mcast_Y (NVLS) or P2P stores to the n_peers tables of peer_Y_host (at most
+ * one of the two).  Forward of dist.PartitionedTrainer: layers 2..K of computer() (main_rec.py:34) restricted to
+ * the mini-batch's receptive field on every rank.  D in {32, 64, 128}. */
+int spex_spmm_csr_rows_exchange_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                                    const float* X, int64_t n_rows, int32_t D,
+                                    const int32_t* rows, int64_t n_sel,
+                                    const int32_t* long_slots, int32_t n_long_sel,
+                                    const int32_t* seg_ids, int32_t n_seg_sel,
+                                    int64_t out_row_offset, float* mcast_Y,
+                                    float* const* peer_Y_host, int32_t n_peers,
+                                    const float* addend, float addend_scale, float* Z, float z_scale,
+                                    const spex_long_plan* plan, void* stream);
 /* Last layer of a row-partitioned propagation with the NEXT call's E^(0) piggy-backed on its epilogue:
  * Z = (addend * addend_scale + A.X) * z_scale (no Y output), and the warp that finishes output row r also
  * copies row r of pub_src (this rank's slice of the next table) to rows out_row_offset + r of every rank's

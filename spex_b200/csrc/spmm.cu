@@ -765,6 +765,42 @@ extern "C" int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col,
   return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, &sub);
 }
 
+// The row-subset layer with the fused exchange of the row-partitioned modes: the listed rows (LOCAL ids of this
+// rank's row block) are computed as in spex_spmm_csr_rows_f32 and their Y rows stored into every rank's
+// next-layer table - one multimem.st per row to mcast_Y (NVLS), or P2P stores to the n_peers tables of
+// peer_Y_host (at most one of the two; neither: local outputs only) - at rows out_row_offset + row.
+// Forward of dist.PartitionedTrainer: layers 2..K of main_rec.py:34's computer() restricted to the batch's
+// receptive field on every rank.
+extern "C" int spex_spmm_csr_rows_exchange_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                                               const float* X, int64_t n_rows, int32_t D, const int32_t* rows,
+                                               int64_t n_sel, const int32_t* long_slots, int32_t n_long_sel,
+                                               const int32_t* seg_ids, int32_t n_seg_sel, int64_t out_row_offset,
+                                               float* mcast_Y, float* const* peer_Y_host, int32_t n_peers,
+                                               const float* addend, float addend_scale, float* Z, float z_scale,
+                                               const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(n_sel < 0 || n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows) || out_row_offset < 0,
+                 SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_long_sel > 0 && (!long_slots || !seg_ids || !plan || n_seg_sel < n_long_sel), SPEX_E_BADARG);
+  SPEX_RETURN_IF(mcast_Y && n_peers > 0, SPEX_E_BADARG);
+  SPEX_RETURN_IF(n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_Y_host), SPEX_E_BADARG);
+  SPEX_RETURN_IF(mcast_Y && !aligned16(mcast_Y), SPEX_E_ALIGN);
+  if (n_sel == 0) return 0;
+  Epilogue ep{};
+  ep.addend = addend;
+  ep.addend_scale = addend_scale;
+  ep.Z = Z;
+  ep.z_scale = z_scale;
+  ep.peer_row_offset = out_row_offset;
+  ep.mcast = mcast_Y;
+  ep.n_peers = mcast_Y ? 0 : n_peers;
+  for (int p = 0; p < ep.n_peers; ++p) {
+    SPEX_RETURN_IF(!peer_Y_host[p] || !aligned16(peer_Y_host[p]), SPEX_E_BADARG);
+    ep.peer[p] = peer_Y_host[p];
+  }
+  RowSubset sub{rows, n_sel, long_slots, n_long_sel, seg_ids, n_seg_sel};
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, &sub);
+}
+
 extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,
                                       const float* X, int64_t n_rows, int32_t D,
                                       int64_t out_row_offset, float* const* peer_Y_host,

@@ -88,6 +88,7 @@ class PartitionedPropagator:
         self.timing = None        # set to [] to collect per-phase CUDA-event pairs (bring-up)
         self._mc = None           # multicast pointers of the tables (mode "mcast")
         self._symm = []
+        self._nnz_global = None   # nnz of the whole matrix (receptive_sets)
         self._slot = 0            # ring slot that holds / receives E^(0) of the next propagate()
         self._staged = None       # (key, event): E^(0) already published into slot self._slot
         self._side = None         # high-priority stream of the background publish
@@ -195,7 +196,20 @@ class PartitionedPropagator:
             dist.all_reduce(self._flag, group=self.group)
 
     # ---- one layer --------------------------------------------------------------------------------
-    def _layer(self, X_full, Y_local, addend, Z_local, z_scale, push_buf=None, publish=None):
+    def _layer(self, X_full, Y_local, addend, Z_local, z_scale, push_buf=None, publish=None, subset=None):
+        if subset is not None:
+            # restricted to a row list (receptive field of a mini-batch), same fused exchange
+            from ._capi import call, ptr, stream_ptr
+
+            rows, slots, segs = subset
+            mc = C.c_void_p(self._mc[push_buf]) if (push_buf is not None and self.mode == "mcast") else None
+            peers = self._peer_ptrs[push_buf] if (push_buf is not None and self.mode == "push") else None
+            call("spex_spmm_csr_rows_exchange_f32", ptr(self.g.rowptr), ptr(self.g.col), ptr(self.g.val), ptr(X_full),
+                 self.g.n_rows, self.D, ptr(rows), rows.numel(), ptr(slots), 0 if slots is None else slots.numel(),
+                 ptr(segs), 0 if segs is None else segs.numel(), self.r0, mc, peers,
+                 self.world if peers is not None else 0, ptr(addend), 1.0, ptr(Z_local), float(z_scale),
+                 self.g.plan(self.D), stream_ptr())
+            return
         if self.local_spmm is not None:
             acc = self.local_spmm(self.g, X_full)
             if Y_local is not None:
@@ -306,9 +320,63 @@ class PartitionedPropagator:
         return (self.mode == "mcast" and self.e0_exchange == "mcast") or \
                (self.mode == "push" and self.e0_exchange == "push")
 
+    # ---- receptive field of a mini-batch (training forward) ------------------------------------------
+    def _own(self, rows_global: torch.Tensor) -> torch.Tensor:
+        m = (rows_global >= self.r0) & (rows_global < self.r1)
+        return rows_global[m] - self.r0
+
+    def _sum_over_ranks(self, x: int) -> int:
+        t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def _all_gather_var(self, t: torch.Tensor) -> torch.Tensor:
+        """Concatenation of every rank's 1-D int64 tensor (lengths differ)."""
+        if self.world == 1:
+            return t
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        pad = torch.zeros(max(max(sizes), 1), dtype=torch.int64, device=self.device)
+        pad[: t.numel()] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:k] for b, k in zip(bufs, sizes)])
+
+    def receptive_sets(self, S: torch.Tensor):
+        """ops.receptive_rows over the partition: R[k] (global row ids, identical on every rank) = the rows of
+        E^(k) that the rows S of the layer mean depend on, or None = all rows.  Every rank expands the rows it
+        owns through its own CSR block (the columns are global ids); the lists are all-gathered."""
+        from . import ops
+
+        K = self.K
+        R = [None] * (K + 1)
+        if (K < 1 or self.mode not in ("push", "mcast") or self.local_spmm is not None
+                or self.D not in (32, 64, 128)):
+            return R
+        if self._nnz_global is None:
+            self._nnz_global = self._sum_over_ranks(self.g.nnz)
+        nnz = self._nnz_global
+        d = self._sum_over_ranks(self.g.degree_sum(self._own(S)))
+        if d > ops.SUBSET_MAX_EDGE_FRAC * nnz:
+            return R
+        R[K] = S
+        cur = S
+        for k in range(K - 1, 0, -1):
+            if d > ops.EXPAND_MAX_EDGE_FRAC * nnz:
+                break
+            cand = torch.unique(torch.cat([S, self._all_gather_var(self.g.neighbors(self._own(cur)))]))
+            d = self._sum_over_ranks(self.g.degree_sum(self._own(cand)))
+            if d > ops.SUBSET_MAX_EDGE_FRAC * nnz:
+                break
+            R[k] = cur = cand
+        return R
+
     def propagate(self, E0_local: torch.Tensor, out: torch.Tensor = None,
                   next_E0_local: torch.Tensor = None, next_ready=None, first_full: torch.Tensor = None,
-                  adam: dict = None) -> torch.Tensor:
+                  adam: dict = None, row_sets=None) -> torch.Tensor:
         """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]
         (written into `out` if given).  `next_E0_local`: this rank's rows of the table of the NEXT
         call, if the caller already has it (an inference / evaluation sweep over many tables, or
@@ -319,7 +387,9 @@ class PartitionedPropagator:
         training step: zero but for the batch's rows, which every rank can compute).
         `adam` (fused modes): {p, m, v, lr, beta1, beta2, eps, step} - the result is not returned but consumed
         as the gradient of `p` by a dense Adam fused into the last layer's epilogue, and the updated rows of
-        `p` are published as the next call's table (spex_spmm_csr_f32_adam)."""
+        `p` are published as the next call's table (spex_spmm_csr_f32_adam).
+        `row_sets` (fused modes; from receptive_sets(S)): layer k computes - and exchanges - only the rows
+        row_sets[k] (None = all); only the rows S = row_sets[K] of the result are then valid."""
         K = self.K
         if out is None:
             out = torch.empty_like(E0_local)
@@ -371,8 +441,13 @@ class PartitionedPropagator:
                 else:
                     self._publish_next(next_E0_local, (a + K) % nt, next_ready)
             if fused:
+                subset = None
+                if row_sets is not None and row_sets[k + 1] is not None:
+                    if publish is not None:
+                        raise ValueError("row_sets cannot be combined with a published next table")
+                    subset = self.g.row_subset(self._own(row_sets[k + 1]))
                 self._layer(X_full, None, addend, out, inv if last else 1.0,
-                            push_buf=None if last else (a + k + 1) % nt, publish=publish)
+                            push_buf=None if last else (a + k + 1) % nt, publish=publish, subset=subset)
                 if publish is not None:
                     done = torch.cuda.Event()
                     done.record()
@@ -539,13 +614,18 @@ class PartitionedTrainer:
         self.out = torch.empty_like(W_local)
         self._dirty = None
         self.t = 0
+        self.receptive_field = True
         self.ops = train_ops if train_ops is not None else _CudaTrainOps()
 
     def step(self, users: torch.Tensor, items: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         p, r0, r1 = self.prop, self.prop.r0, self.prop.r1
-        out = p.propagate(self.W, out=self.out)
         B = users.numel()
         rows = torch.cat([users, items + self.nur]).to(torch.int64)
+        # forward restricted to the batch's receptive field (fused modes; every computed row is bit-identical to
+        # the full computer(), so loss, gradients and weights are unchanged): layer K on the batch's rows, layer
+        # K-1 on their neighbours, ... - the backward still runs all rows
+        sets = p.receptive_sets(torch.unique(rows)) if (self.receptive_field and self.fused) else None
+        out = p.propagate(self.W, out=self.out, row_sets=sets)
         R = self.ops.gather_owned(out, rows, r0, r1)
         if p.world > 1:
             dist.all_reduce(R, group=p.group)

@@ -170,6 +170,50 @@ def _train_worker(rank, world, port, q):
             werr = float((tr.W - W_ref[r0:r1]).abs().max() / W_ref.abs().max())
             res[mode] = (losses[0] == ref_losses[0], max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)), werr)
             prop.close()
+        # receptive-field forward of the partitioned trainer (layers restricted to the rows the batch depends on,
+        # fused exchange of the restricted rows): a graph large enough for the restriction to engage; weights
+        # after three Adam steps bit-equal to the unrestricted partitioned trainer, and to the single-GPU model
+        ds2 = SyntheticDataset(20000, 8000, 150000, seed=8)
+        torch.manual_seed(11)
+        model2 = LightGCN(make_args(), ds2).to(dev)
+        W20 = model2._table.detach().clone()
+        opt2 = FusedAdam(model2.parameters(), lr=1e-2)
+        b2 = []
+        for _ in range(3):
+            u2 = torch.from_numpy(rng.integers(0, ds2.n_users, 48)).to(dev)
+            i2 = torch.from_numpy(rng.integers(0, ds2.m_items, 48)).to(dev)
+            l2 = torch.from_numpy(rng.integers(0, 2, 48)).float().to(dev)
+            b2.append((u2, i2, l2))
+            model2.train()
+            opt2.zero_grad(set_to_none=True)
+            lo2 = model2(u2, i2, l2, flag=0)
+            lo2.backward()
+            opt2.step()
+        W2_ref = model2._table.detach().clone()
+        full2 = model2.device_graph()
+        gh2 = ds2.getCSR()
+        N2 = full2.n_rows
+        bounds2 = partition_rows_by_nnz(gh2.rowptr, world)
+        a0, a1 = bounds2[rank], bounds2[rank + 1]
+        lo_, hi_ = int(gh2.rowptr[a0]), int(gh2.rowptr[a1])
+        lg2 = ops.DeviceGraph((full2.rowptr[a0: a1 + 1] - lo_).contiguous(), full2.col[lo_:hi_].clone(),
+                              full2.val[lo_:hi_].clone(), N2, None, 32, row_offset=a0)   # seg_len 32: long rows too
+        got = {}
+        for rf in (False, True):
+            prop = PartitionedPropagator(lg2, bounds2, D, K, mode="push", device=dev)
+            prop.e0_exchange = "push"
+            tr = PartitionedTrainer(prop, W20[a0:a1].clone(), ds2.n_users + 1, lr=1e-2)
+            tr.receptive_field = rf
+            if rf:
+                S2 = torch.unique(torch.cat([b2[0][0], b2[0][1] + ds2.n_users + 1]))
+                sets = prop.receptive_sets(S2)
+                engaged = sets[K] is not None and sets[K - 1] is not None
+            ls = [float(tr.step(*b)) for b in b2]
+            torch.cuda.synchronize()
+            got[rf] = (ls, tr.W.clone())
+            prop.close()
+        werr2 = float((got[True][1] - W2_ref[a0:a1]).abs().max() / W2_ref.abs().max())
+        res["receptive"] = (engaged, got[True][0] == got[False][0], bool(torch.equal(got[True][1], got[False][1])), werr2)
         # evaluation sharded by user against the single-GPU ranking
         model.eval()
         users_all = torch.arange(ds.n_users, device=dev)
@@ -211,5 +255,7 @@ def test_partitioned_training_and_sharded_eval_match_single_gpu():
             first_equal, lerr, werr = res[mode]
             assert first_equal, (rank, mode)             # same arithmetic on the assembled rows: bit-equal loss
             assert lerr < 1e-5 and werr < 1e-5, (rank, mode, lerr, werr)
+        engaged, same_loss, same_w, werr2 = res["receptive"]
+        assert engaged and same_loss and same_w and werr2 < 1e-5, (rank, res["receptive"])
         same, dr, dn = res["eval"]
         assert same and dr < 1e-12 and dn < 1e-12, (rank, res["eval"])
