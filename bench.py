@@ -1056,9 +1056,10 @@ def run_ours(args):
         trainj = {"metric": "lightgcn_train_step_ms", "value": ms_tr, "unit": "ms", "higher_is_better": False,
                   "steps_per_s": 1e3 / ms_tr, "batch": Bt, "loss": loss_rf,
                   "receptive_field": {"rows_per_layer": [None if r is None else int(r.numel()) for r in sets[1:]],
-                                      "note": "FORWARD layers restricted to the rows the batch depends on (null = all "
+                                      "note": "forward layers restricted to the rows the batch depends on (null = all "
                                               "rows), restricted rows exchanged by the same fused epilogue; the "
-                                              "backward runs all rows; loss and weights bit-identical to the full step"},
+                                              "backward mirrors it (first layer restricted, written into zeroed "
+                                              "tables); loss and weights bit-identical to the full step"},
                   "full_computer_step": {"value": ms_tr_full, "unit": "ms", "loss": loss_full,
                                          "same_loss_as_receptive_path": loss_full == loss_rf},
                   # edges actually traversed per second: quoted on the FULL step

@@ -345,6 +345,12 @@ class PartitionedPropagator:
         dist.all_gather(bufs, pad, group=self.group)
         return torch.cat([b[:k] for b, k in zip(bufs, sizes)])
 
+    def zero_slot(self, j: int):
+        """Zero this rank's copy of the ring slot that layer j of the NEXT propagate() writes (a restricted layer
+        stores only its rows; the rest of a gradient table must read as zero).  Call it before a collective that
+        every rank passes before that propagate(): peers push into the slot only afterwards."""
+        self._X[(self._slot + j) % self.n_tables].zero_()
+
     def receptive_sets(self, S: torch.Tensor):
         """ops.receptive_rows over the partition: R[k] (global row ids, identical on every rank) = the rows of
         E^(k) that the rows S of the layer mean depend on, or None = all rows.  Every rank expands the rows it
@@ -615,6 +621,7 @@ class PartitionedTrainer:
         self._dirty = None
         self.t = 0
         self.receptive_field = True
+        self.receptive_backward = True
         self.ops = train_ops if train_ops is not None else _CudaTrainOps()
 
     def step(self, users: torch.Tensor, items: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
@@ -623,10 +630,20 @@ class PartitionedTrainer:
         rows = torch.cat([users, items + self.nur]).to(torch.int64)
         # forward restricted to the batch's receptive field (fused modes; every computed row is bit-identical to
         # the full computer(), so loss, gradients and weights are unchanged): layer K on the batch's rows, layer
-        # K-1 on their neighbours, ... - the backward still runs all rows
+        # K-1 on their neighbours, ...; the backward mirrors it (below)
         sets = p.receptive_sets(torch.unique(rows)) if (self.receptive_field and self.fused) else None
         out = p.propagate(self.W, out=self.out, row_sets=sets)
         R = self.ops.gather_owned(out, rows, r0, r1)
+        # backward mirror of the receptive field: H_j = g + A^T H_{j-1} is non-zero only on sets[K - j], so layer j
+        # (j < K) computes and exchanges those rows into a zeroed table (zeroed here, before the all-reduce that
+        # orders it ahead of every peer's stores)
+        bsets = None
+        if sets is not None and self.fused and self.receptive_backward:
+            bsets = [None] * (p.K + 1)
+            for j in range(1, p.K):
+                if sets[p.K - j] is not None:
+                    bsets[j] = sets[p.K - j]
+                    p.zero_slot(j)
         if p.world > 1:
             dist.all_reduce(R, group=p.group)
         Ru, Ri = R[:B], R[B:]
@@ -643,7 +660,9 @@ class PartitionedTrainer:
             self.ops.scatter(rows[:B], Ri, dgamma, self.G_full, 0, 0)
             self.ops.scatter(rows[B:], Ru, dgamma, self.G_full, 0, 0)
             self._dirty = rows
-            p.propagate(self.G_full[r0:r1], out=self.dW, first_full=self.G_full,
+            if bsets is not None and any(b is not None for b in bsets):
+                self.dW.zero_()     # a restricted first layer writes g + A g on its rows only; the rest is 0
+            p.propagate(self.G_full[r0:r1], out=self.dW, first_full=self.G_full, row_sets=bsets,
                         adam={"p": self.W, "m": self.m, "v": self.v, "lr": self.lr, "beta1": self.betas[0],
                               "beta2": self.betas[1], "eps": self.eps, "step": self.t})
             return loss
