@@ -705,6 +705,8 @@ class ShardedEvaluator:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.D = I_all.shape[1]
+        if scorer == "f16" and not ops.f16_filter_is_selective(U_all, I_all, torch.arange(U_all.shape[0], device=I_all.device)):
+            scorer = self.scorer = "fp32"      # near-equal scores: the exact scorer is the faster exact path
         if scorer == "f16":
             self.Ih, self.m_pad, self.imeta = ops.pack_f16(I_all, None, ops.TC_ITEM_MULTIPLE)
         elif scorer == "bf16":

@@ -251,11 +251,12 @@ class LightGCN(BasicModel):
 
     @torch.no_grad()
     def rank_topk(self, users, k: int = 20, exclude_train: bool = True, precision: str = "f16",
-                  user_block: int = 1 << 16):
+                  user_block: int = 1 << 16, probe: bool = True):
         """Full-ranking top-k items per user: (idx int32 [B,k], score fp32 [B,k]).
 
         precision "f16":  tcgen05 fp16-accumulator filter + exact fp32 re-score of the survivors
-                          (operands fp16(x 2^s); recdim 64 or 128) - the default;
+                          (operands fp16(x 2^s); recdim 64 or 128) - the default; a probe
+                          (ops.f16_filter_is_selective) routes tables with near-equal scores to "fp32";
         precision "bf16": round 1's tcgen05 GEMM, bf16 operands / fp32 accumulators (recdim 64);
         precision "fp32": exact CUDA-core scorer (bit-exact ordering, any recdim).
         Ordering: score descending, ties by ascending item id; masked = the user's train items.
@@ -274,6 +275,9 @@ class LightGCN(BasicModel):
             raise RuntimeError("the bf16 tcgen05 scorer is built for recdim == 64")
         if precision == "f16" and self.latent_dim not in (64, 128):
             raise RuntimeError("the f16 tcgen05 scorer is built for recdim 64 or 128")
+        if precision == "f16" and probe and not ops.f16_filter_is_selective(all_users, all_items, users):
+            # degenerate score distribution (near-ties everywhere): the exact scorer is the faster exact path
+            return ops.score_topk_f32(all_users, all_items, users, k, mrp, mcol)
         if self._item_pack is None or self.training or self._item_pack[0] != precision:
             if precision == "f16":
                 self._item_pack = (precision,) + ops.pack_f16(all_items, None, ops.TC_ITEM_MULTIPLE)

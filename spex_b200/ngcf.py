@@ -199,7 +199,8 @@ class Model_Wrapper(nn.Module):
         return self.rec_loss_function(predict, real)
 
     @torch.no_grad()
-    def rank_topk(self, users, k: int = 20, mask_rowptr=None, mask_col=None, precision: str = "f16"):
+    def rank_topk(self, users, k: int = 20, mask_rowptr=None, mask_col=None, precision: str = "f16",
+                  probe: bool = True):
         """Top-k items per user over the concatenated layer outputs (utility/batch_test.py:158 followed by
         the ranking): tcgen05 fp16-accumulator filter + exact fp32 re-score at D = 64 (L + 1), or the exact
         fp32 CUDA-core scorer (precision "fp32").  Returns (idx int32 [B, k], score fp32 [B, k])."""
@@ -207,7 +208,8 @@ class Model_Wrapper(nn.Module):
         ua, ia = ua.contiguous(), ia.contiguous()
         users = torch.as_tensor(users, device=ua.device).long().contiguous()
         Dk = ua.shape[1]
-        if precision == "fp32" or Dk not in (64, 128):
+        if precision == "fp32" or Dk not in (64, 128) or (probe and not ops.f16_filter_is_selective(ua, ia, users)):
+            # (an untrained NGCF's normalised outputs are almost parallel: near-ties everywhere, no filter helps)
             return ops.score_topk_f32(ua, ia, users, k, mask_rowptr, mask_col)
         Ih, m_pad, imeta = ops.pack_f16(ia, None, ops.TC_ITEM_MULTIPLE)
         Uh, b_pad, umeta = ops.pack_f16(ua, users, ops.TC_USER_MULTIPLE)

@@ -791,6 +791,32 @@ def rating_dense(U, I, users, apply_sigmoid: bool = True):
     return out
 
 
+def f16_filter_is_selective(U, I, users, n_users: int = 64, n_items: int = 8192, seed: int = 0) -> bool:
+    """Probe for spex_score_topk_f16.  Its fp16-accumulated score only FILTERS: everything within 2 eps of a
+    row's k-th best (eps = 2^-9 |u| max|v|) is re-scored exactly, one row at a time.  On tables whose scores are
+    nearly equal across items - an untrained NGCF model, whose normalised layer outputs are almost parallel:
+    measured 99 ms against 1.7 ms for random tables of the same shape and 7 ms for the exact fp32 scorer - that
+    band holds most items and the filter degenerates.  The probe scores a sample (n_users x n_items, exact fp32,
+    spex_rating_f32) and compares the band with the spread of each user's scores: selective iff the median of
+    2 eps / (max - median score) stays below 0.1 (random / trained tables: ~0.01).  Callers fall back to the exact
+    fp32 scorer otherwise; the result is the same ranking either way."""
+    _need_cuda(U, I)
+    dev = U.device
+    users = _i64c(users, dev)
+    if users.numel() == 0 or I.shape[0] < 64:
+        return True
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    us = users[torch.randint(0, users.numel(), (min(n_users, users.numel()),), device=dev, generator=g)]
+    it = torch.randint(0, I.shape[0], (min(n_items, I.shape[0]),), device=dev, generator=g)
+    Is = I[it].contiguous()
+    s = rating_dense(U, Is, us, apply_sigmoid=False)
+    spread = s.max(dim=1).values - s.median(dim=1).values
+    eps = (1.0 / 512.0) * U[us].norm(dim=1) * Is.norm(dim=1).max()
+    ratio = 2.0 * eps / spread.clamp_min(1e-30)
+    return bool(ratio.median() < 0.1)
+
+
 TC_USER_MULTIPLE = 128   # users per CTA of the tcgen05 scorer (UMMA M)
 TC_MAX_K = 64            # larger k: score_topk_f32
 TC_ITEM_MULTIPLE = 128   # items per tile (UMMA N)

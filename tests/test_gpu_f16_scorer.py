@@ -177,3 +177,18 @@ def test_model_rank_topk_f16_vs_fp32_and_metrics(cuda_device):
         assert abs(m32[key] - mo[key]) <= 1.0 / n_users, (key, m32, mo)
         assert abs(m16[key] - mo[key]) <= 2.0 / n_users, (key, m16, mo)     # fp16 operands: near-tie swaps only
         assert abs(mb[key] - mo[key]) <= 6.0 / n_users, (key, mb, mo)       # bf16 operands: 8x coarser
+
+
+def test_near_tie_probe(cuda_device):
+    """ops.f16_filter_is_selective: random tables keep the tensor-core filter, tables whose items are almost
+    parallel (every score within the filter's error band of the k-th best) go to the exact scorer."""
+    from spex_b200 import ops
+
+    torch.manual_seed(5)
+    U = torch.randn(500, 64, device=cuda_device)
+    I = torch.randn(20000, 64, device=cuda_device)
+    users = torch.arange(500, device=cuda_device)
+    assert ops.f16_filter_is_selective(U, I, users)
+    base = torch.randn(1, 64, device=cuda_device)
+    I2 = base + 1e-4 * torch.randn(20000, 64, device=cuda_device)       # near-collinear items
+    assert not ops.f16_filter_is_selective(U, I2, users)
