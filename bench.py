@@ -285,6 +285,7 @@ def bench_small_configs(torch, dev):
 
     import numpy as np
 
+    from spex_b200 import ops as ops_
     from spex_b200.dataloader import SyntheticDataset
     from spex_b200.optim import FusedAdam
 
@@ -383,14 +384,26 @@ def bench_small_configs(torch, dev):
         ng.eval()
         ng.rank_topk(torch.arange(nu2, device=dev), k=20)
 
+    def ngcf_rank_tc():
+        ng.eval()
+        ng.rank_topk(torch.arange(nu2, device=dev), k=20, probe=False)
+
     ms_inf = timed(ngcf_infer, 10)
     ms_tr = timed(ngcf_train, 5)
     ms_rank = timed(ngcf_rank, 3)
+    ms_rank_tc = timed(ngcf_rank_tc, 2, warm=1)
+    ng.eval()
+    with torch.no_grad():
+        ua_, ia_ = ng.propagate()
+        selective = ops_.f16_filter_is_selective(ua_.contiguous(), ia_.contiguous(), torch.arange(nu2, device=dev))
     out["configs[2] NGCF twitter-shaped"] = {
         "workload": f"{nu2} users x {m2} items, {ds2.trainDataSize} interactions, nnz(D^-1(A+I))={adj.nnz}, 1 layer, "
                     "outputs [N, 128]", "propagation_forward_ms": round(ms_inf, 4),
         "propagation_gedges_per_s": adj.nnz / (ms_inf * 1e-3) / 1e9, "train_step_ms_batch1024": round(ms_tr, 3),
         "fullrank_top20_all_users_ms": round(ms_rank, 3), "fullrank_users_per_s": nu2 / (ms_rank * 1e-3),
+        "fullrank_scorer": "f16 tcgen05 (D=128)" if selective else "exact fp32 (the near-tie probe routed it: the random-init "
+                           "model's normalised outputs are almost parallel, every score ties within the fp16 filter band)",
+        "fullrank_top20_forced_tcgen05_ms": round(ms_rank_tc, 3),
         "scorer_tflops_d128": 2.0 * nu2 * m2 * 128 / (ms_rank * 1e-3) / 1e12}
     return out
 
