@@ -47,6 +47,33 @@ def test_spmm_matches_sparse_mm(cuda_device, D, seg_len):
     assert rel_err(Z, (add * 2 + ref) * 0.25) < TOL
 
 
+@pytest.mark.parametrize("D", [64, 32, 128])
+def test_spmm_16_byte_aligned_table_takes_the_128_bit_kernels(cuda_device, D):
+    """A table that is only 16-byte aligned (the ABI's minimum) cannot use the 256-bit gathers: the library falls
+    back to the 128-bit kernels.  Same result as the 32-byte aligned table to fp32 rounding (the two kernels sum a
+    row in different fixed orders), both within tolerance of torch.sparse.mm, and each bit-reproducible."""
+    from spex_b200 import ops
+
+    nu, m = 700, 400
+    u, i = random_graph(nu, m, 9000, 11, hub_items=3, hub_degree=500)
+    A = oracle_graph(u, i, nu + 1, m)
+    g = _dev_graph(u, i, nu + 1, m, cuda_device, 32)
+    N = nu + 1 + m
+    torch.manual_seed(1)
+    X = torch.randn(N, D)
+    ref = torch.sparse.mm(A, X)
+    big = torch.empty(N * D + 4, device=cuda_device)
+    Xu = big[4:].view(N, D)
+    Xu.copy_(X)
+    assert Xu.data_ptr() % 32 == 16
+    Xa = X.to(cuda_device)
+    assert Xa.data_ptr() % 32 == 0
+    Yu, Ya = ops.spmm(g, Xu), ops.spmm(g, Xa)
+    assert rel_err(Yu, ref) < TOL and rel_err(Ya, ref) < TOL
+    assert rel_err(Yu, Ya) < 1e-6
+    assert torch.equal(ops.spmm(g, Xu), Yu) and torch.equal(ops.spmm(g, Xa), Ya)
+
+
 @pytest.mark.parametrize("seg_len", [32, 256])
 def test_spmm_column_blocked_long_rows(cuda_device, seg_len, monkeypatch):
     """Long rows cut at column-block boundaries and launched block-major (the L2-window path used
