@@ -113,6 +113,12 @@ int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, const float* va
  *   rows        int32 [n_sel]       row ids (no duplicates, any order)
  *   long_slots  int32 [n_long_sel]  for the listed rows of degree > plan->seg_len: their positions in
  *                                   plan->long_rows; seg_ids int32 [n_seg_sel]: the ids of all their segments
+ *   n_sel < 0                       all rows (rows / long_slots / seg_ids unused)
+ *   x_nonzero   uint8 [n_cols]      optional: X is known to be ZERO (+0.0 in every element) on the rows c with
+ *                                   x_nonzero[c] == 0 - the second layer of the training backward reads
+ *                                   H_1 = g + A^T g, non-zero only on the batch's rows and their neighbours.  Those
+ *                                   gathers are skipped; the result is bit-identical to the dense layer (the
+ *                                   skipped terms are val * (+0)).  Used with 32-byte aligned tables, else ignored.
  * D in {32, 64, 128}.
  */
 int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col, const float* val,
@@ -120,6 +126,7 @@ int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col, const floa
                            const int32_t* rows, int64_t n_sel,
                            const int32_t* long_slots, int32_t n_long_sel,
                            const int32_t* seg_ids, int32_t n_seg_sel,
+                           const uint8_t* x_nonzero,
                            float* Y, const float* addend, float addend_scale,
                            float* Z, float z_scale,
                            const spex_long_plan* plan, void* stream);
@@ -430,12 +437,14 @@ int spex_mcast_rows_f32_ex(const float* src, int64_t n_rows, int32_t D, int64_t 
  * rank's row block) are computed and their Y rows stored at rows out_row_offset + row of every rank's next-layer
  * table - one multimem.st per row to mcast_Y (NVLS) or P2P stores to the n_peers tables of peer_Y_host (at most
  * one of the two).  Forward of dist.PartitionedTrainer: layers 2..K of computer() (main_rec.py:34) restricted to
- * the mini-batch's receptive field on every rank.  D in {32, 64, 128}. */
+ * the mini-batch's receptive field on every rank; n_sel < 0 = all rows, x_nonzero as above (second backward
+ * layer).  D in {32, 64, 128}. */
 int spex_spmm_csr_rows_exchange_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                                     const float* X, int64_t n_rows, int32_t D,
                                     const int32_t* rows, int64_t n_sel,
                                     const int32_t* long_slots, int32_t n_long_sel,
                                     const int32_t* seg_ids, int32_t n_seg_sel,
+                                    const uint8_t* x_nonzero,
                                     int64_t out_row_offset, float* mcast_Y,
                                     float* const* peer_Y_host, int32_t n_peers,
                                     const float* addend, float addend_scale, float* Z, float z_scale,

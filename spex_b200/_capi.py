@@ -48,10 +48,10 @@ SIGNATURES = {
     "spex_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "spex_launch_count": (_i64, []),
     "spex_spmm_csr_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _f, _p, _f, _PLAN, _p]),
-    "spex_spmm_csr_rows_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _p, _p, _f, _p, _f,
+    "spex_spmm_csr_rows_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _p, _p, _p, _f, _p, _f,
                                          _PLAN, _p]),
-    "spex_spmm_csr_rows_exchange_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _i64, _p, _p,
-                                                  _i32, _p, _f, _p, _f, _PLAN, _p]),
+    "spex_spmm_csr_rows_exchange_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _p, _i64, _p,
+                                                  _p, _i32, _p, _f, _p, _f, _PLAN, _p]),
     "spex_propagate_mean_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _PLAN, _p]),
     "spex_propagate_mean_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _PLAN, _p]),
     "spex_gather_f32": (C.c_int, [_p, _p, _p, _f, _p, _i64, _p]),

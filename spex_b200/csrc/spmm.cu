@@ -254,10 +254,109 @@ __device__ __forceinline__ float4 warp_row_accumulate8(const int32_t* __restrict
 #ifndef SPEX_V8_MINB
 #define SPEX_V8_MINB 32
 #endif
-// kV8: 256-bit gathers (table 32-byte aligned), else the 128-bit version
-template <int D, int U, bool kHot, bool kV8>
+// The same sum when most rows of X are known to be ZERO (nz[c] != 0 marks the rows that may be non-zero): the
+// second layer of the training backward reads H_1 = g + A^T g, which is non-zero only on the batch's rows and
+// their neighbours (~8 % of the edges on the bench graph).  Every lane looks up the byte of its own edge, one
+// ballot gives the batch's active edges, and every lane group walks the active edges AMONG ITS OWN eight in
+// ascending order - the edges the dense kernel would give it, in the same order, minus terms val * (+0) that
+// cannot change a sum (values and zero rows are non-negative zeros) - so the result is bit-identical to the
+// dense kernel's.  (col, val) run two batches ahead and the mask byte one batch ahead, so a batch still exposes
+// a single dependent latency (its gathers).
+template <int D, bool kHot>
+__device__ __forceinline__ float4 warp_row_accumulate8_masked(const int32_t* __restrict__ col,
+                                                              const float* __restrict__ val,
+                                                              const float* __restrict__ X,
+                                                              const uint8_t* __restrict__ nz, int64_t start,
+                                                              int64_t end, int lane) {
+  constexpr int LPR8 = D / 8;
+  constexpr int U = D >= 64 ? 4 : 2;
+  const int grp = lane / LPR8, sub = lane % LPR8;
+  const float* Xs = X + sub * 8;
+  f8 acc;
+  acc.a = f4_zero();
+  acc.b = f4_zero();
+  int rem = (int)(end - start);
+  const int32_t* cp = col + start + lane;
+  const float* vp = val + start + lane;
+  constexpr uint32_t kIdMask = kHot ? 0x7fffffffu : 0xffffffffu;
+  int c = 0, cn = 0;
+  float v = 0.f, vn = 0.f;
+  bool on = false;
+  if (lane < rem) {
+    c = ld_stream_s32(cp);
+    v = ld_stream_f32(vp);
+  }
+  if (lane + 32 < rem) {
+    cn = ld_stream_s32(cp + 32);
+    vn = ld_stream_f32(vp + 32);
+  }
+  if (lane < rem) on = nz[(uint32_t)c & kIdMask] != 0;
+  while (rem > 0) {
+    int c2 = 0;
+    float v2 = 0.f;
+    if (lane + 64 < rem) {
+      c2 = ld_stream_s32(cp + 64);
+      v2 = ld_stream_f32(vp + 64);
+    }
+    bool onn = false;
+    if (lane + 32 < rem) onn = nz[(uint32_t)cn & kIdMask] != 0;
+    const unsigned act = __ballot_sync(kFull, on);
+    unsigned mine = (act >> (grp * LPR8)) & (LPR8 == 32 ? 0xffffffffu : ((1u << LPR8) - 1u));
+#pragma unroll 1
+    while (__any_sync(kFull, mine != 0)) {
+      f8 x[U];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool has = mine != 0;
+        const int src = grp * LPR8 + (has ? __ffs(mine) - 1 : 0);
+        mine &= mine - 1;
+        const int cc = __shfl_sync(kFull, c, src);
+        vv[u] = __shfl_sync(kFull, v, src);
+        if (has) {
+          x[u] = gather_row8<D, kHot>(Xs, cc);
+        } else {
+          x[u].a = f4_zero();
+          x[u].b = f4_zero();
+          vv[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) f8_fma(acc, vv[u], x[u]);
+    }
+    c = cn;
+    v = vn;
+    on = onn;
+    cn = c2;
+    vn = v2;
+    cp += 32;
+    vp += 32;
+    rem -= 32;
+  }
+#pragma unroll
+  for (int m = LPR8; m < 32; m <<= 1) {
+    f4_add(acc.a, f4_shfl_xor(acc.a, m));
+    f4_add(acc.b, f4_shfl_xor(acc.b, m));
+  }
+  const int src = (lane >> 1) & (LPR8 - 1);
+  float4 lo, hi;
+  lo.x = __shfl_sync(kFull, acc.a.x, src);
+  lo.y = __shfl_sync(kFull, acc.a.y, src);
+  lo.z = __shfl_sync(kFull, acc.a.z, src);
+  lo.w = __shfl_sync(kFull, acc.a.w, src);
+  hi.x = __shfl_sync(kFull, acc.b.x, src);
+  hi.y = __shfl_sync(kFull, acc.b.y, src);
+  hi.z = __shfl_sync(kFull, acc.b.z, src);
+  hi.w = __shfl_sync(kFull, acc.b.w, src);
+  return (lane & 1) ? hi : lo;
+}
+
+// kV8: 256-bit gathers (table 32-byte aligned), else the 128-bit version; kMask (with kV8): X is zero outside nz
+template <int D, int U, bool kHot, bool kV8, bool kMask = false>
 __device__ __forceinline__ float4 row_sum(const int32_t* __restrict__ col, const float* __restrict__ val,
-                                          const float* __restrict__ X, int64_t start, int64_t end, int lane) {
+                                          const float* __restrict__ X, int64_t start, int64_t end, int lane,
+                                          const uint8_t* __restrict__ nz = nullptr) {
+  if (kV8 && kMask) return warp_row_accumulate8_masked<D, kHot>(col, val, X, nz, start, end, lane);
   if (kV8) return warp_row_accumulate8<D, (D >= 64 ? SPEX_V8_U : D / 8), kHot>(col, val, X, start, end, lane);
   return warp_row_accumulate<D, U, 0, false, kHot>(col, val, X, start, end, lane);
 }
@@ -365,12 +464,12 @@ __device__ __forceinline__ void row_epilogue(const Epilogue& ep, float4 acc, int
 // backfill every slot (32 CTAs = 32 warps per SM at 63 registers).
 constexpr int kRowsPerCta = SPEX_ROWS_PER_CTA;  // warps (= rows) per CTA
 
-template <int D, int U, bool kHot, bool kV8>
+template <int D, int U, bool kHot, bool kV8, bool kMask>
 __global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ X, int64_t n_rows,
                  int32_t skip_longer_than, Epilogue ep, const int64_t* __restrict__ rowmid, int pass,
-                 int64_t split, const int32_t* __restrict__ row_sel) {
+                 int64_t split, const int32_t* __restrict__ row_sel, const uint8_t* __restrict__ nz) {
   const int lane = threadIdx.x & 31;
   int64_t row = (int64_t)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -388,18 +487,19 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
   // two-pass rows: pass 1 = hot edges [start, rowmid), pass 2 = cold edges [rowmid, end)
   if (pass == 1) end = rowmid[row];
   if (pass == 2) start = rowmid[row];
-  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, end, lane);
+  const float4 acc = row_sum<D, U, kHot, kV8, kMask>(col, val, X, start, end, lane, nz);
   row_epilogue<D>(ep, acc, row, lane);
 }
 
 // warp per segment of a long row -> partial[seg, :]
-template <int D, int U, bool kHot, bool kV8>
+template <int D, int U, bool kHot, bool kV8, bool kMask>
 __global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, const float* __restrict__ X,
                      const int32_t* __restrict__ long_rows,
                      const int32_t* __restrict__ long_segptr, int32_t n_long, int32_t n_seg,
-                     int32_t seg_len, float* __restrict__ partial, const int32_t* __restrict__ seg_sel) {
+                     int32_t seg_len, float* __restrict__ partial, const int32_t* __restrict__ seg_sel,
+                     const uint8_t* __restrict__ nz) {
   constexpr int LPR = RowShape<D>::LPR;
   const int lane = threadIdx.x & 31;
   int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
@@ -416,7 +516,7 @@ spmm_long_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restri
   const int64_t rs = rowptr[row], re = rowptr[row + 1];
   const int64_t start = rs + (int64_t)k * seg_len;
   const int64_t end = (start + seg_len < re) ? start + seg_len : re;
-  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, end, lane);
+  const float4 acc = row_sum<D, U, kHot, kV8, kMask>(col, val, X, start, end, lane, nz);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -441,19 +541,19 @@ spmm_long_fix_kernel(const int32_t* __restrict__ long_rows,
 // block-major order: at any moment the resident warps gather from one ~32 MB window of the
 // table, which the 126 MB L2 keeps resident, so each table row of the window comes from HBM once
 // instead of once per edge.  warp per (row, column block) segment -> partial[seg, :]
-template <int D, int U, bool kHot, bool kV8>
+template <int D, int U, bool kHot, bool kV8, bool kMask>
 __global__ void __launch_bounds__(kRowsPerCta * 32, SPEX_V8_MINB / kRowsPerCta)
 spmm_seg_list_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
                      const float* __restrict__ X, const int64_t* __restrict__ seg_start,
                      const int32_t* __restrict__ seg_count, int32_t n_seg, float* __restrict__ partial,
-                     const int32_t* __restrict__ seg_sel) {
+                     const int32_t* __restrict__ seg_sel, const uint8_t* __restrict__ nz) {
   constexpr int LPR = RowShape<D>::LPR;
   const int lane = threadIdx.x & 31;
   int seg = blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   if (seg_sel) seg = seg_sel[seg];   // subset: n_seg = length of the list
   const int64_t start = seg_start[seg];
-  const float4 acc = row_sum<D, U, kHot, kV8>(col, val, X, start, start + seg_count[seg], lane);
+  const float4 acc = row_sum<D, U, kHot, kV8, kMask>(col, val, X, start, start + seg_count[seg], lane, nz);
   if (lane < LPR) *reinterpret_cast<float4*>(partial + (int64_t)seg * D + lane * 4) = acc;
 }
 
@@ -547,10 +647,10 @@ struct RowSubset {
   int32_t n_seg;
 };
 
-template <int D, int U, bool kHot, bool kV8>
+template <int D, int U, bool kHot, bool kV8, bool kMask>
 static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                         int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
-                        cudaStream_t st, const RowSubset* sub) {
+                        cudaStream_t st, const RowSubset* sub, const uint8_t* nz) {
   const bool rows_only = g_rows_only;
   const bool has_long = plan && plan->n_long > 0;
   const int64_t n_work = sub ? sub->n_rows : n_rows;
@@ -561,25 +661,25 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
                             ? plan->interleave_split
                             : 0;
   const int32_t* row_sel = sub ? sub->rows : nullptr;
-  if (!sub && kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
+  if (!sub && !kMask && kHot && plan && (plan->flags & SPEX_PLAN_TWO_PASS) && plan->rowmid && plan->hot_partial) {
     const int64_t nA = plan->n_split_rows < n_rows ? plan->n_split_rows : n_rows;
     Epilogue epA{};
     epA.Y = plan->hot_partial;
     const int64_t gridA = (nA + kRowsPerCta - 1) / kRowsPerCta;
     if (gridA > 0) {
-      spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
-          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0, nullptr);
+      spmm_rows_kernel<D, U, kHot, kV8, false><<<(unsigned)gridA, kRowsPerCta * 32, 0, st>>>(
+          rowptr, col, val, X, nA, has_long ? plan->seg_len : 0, epA, plan->rowmid, 1, 0, nullptr, nullptr);
       count_launch();
     }
     Epilogue epB = ep;
     epB.partial_in = plan->hot_partial;
     epB.n_partial = nA;
-    spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split, nullptr);
+    spmm_rows_kernel<D, U, kHot, kV8, false><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+        rowptr, col, val, X, n_rows, has_long ? plan->seg_len : 0, epB, plan->rowmid, 2, split, nullptr, nullptr);
     count_launch();
   } else if (grid > 0) {
-    spmm_rows_kernel<D, U, kHot, kV8><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
-        rowptr, col, val, X, n_work, has_long ? plan->seg_len : 0, ep, nullptr, 0, split, row_sel);
+    spmm_rows_kernel<D, U, kHot, kV8, kMask><<<(unsigned)grid, kRowsPerCta * 32, 0, st>>>(
+        rowptr, col, val, X, n_work, has_long ? plan->seg_len : 0, ep, nullptr, 0, split, row_sel, nz);
     count_launch();
   }
   if (rows_only) return check_last();
@@ -592,14 +692,14 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
     const int gs = (n_seg + kRowsPerCta - 1) / kRowsPerCta;
     const int gf = (n_long + kRowsPerCta - 1) / kRowsPerCta;
     if (plan->seg_start) {   // explicit segment list (column-blocked hubs + fixed-length rest)
-      spmm_seg_list_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
-          col, val, X, plan->seg_start, plan->seg_count, n_seg, plan->partial, seg_sel);
+      spmm_seg_list_kernel<D, U, kHot, kV8, kMask><<<gs, kRowsPerCta * 32, 0, st>>>(
+          col, val, X, plan->seg_start, plan->seg_count, n_seg, plan->partial, seg_sel, nz);
       spmm_long_fix_list_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
           plan->long_rows, plan->long_segptr, plan->row_seg, n_long, plan->partial, ep, slot_sel);
     } else {                 // fixed-length segmentation
-      spmm_long_seg_kernel<D, U, kHot, kV8><<<gs, kRowsPerCta * 32, 0, st>>>(
+      spmm_long_seg_kernel<D, U, kHot, kV8, kMask><<<gs, kRowsPerCta * 32, 0, st>>>(
           rowptr, col, val, X, plan->long_rows, plan->long_segptr, plan->n_long, n_seg,
-          plan->seg_len, plan->partial, seg_sel);
+          plan->seg_len, plan->partial, seg_sel, nz);
       spmm_long_fix_kernel<D, U><<<gf, kRowsPerCta * 32, 0, st>>>(
           plan->long_rows, plan->long_segptr, n_long, plan->partial, ep, slot_sel);
     }
@@ -611,7 +711,7 @@ static int launch_vec_h(const int64_t* rowptr, const int32_t* col, const float* 
 template <int D, int U>
 static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                       int64_t n_rows, const Epilogue& ep, const spex_long_plan* plan,
-                      cudaStream_t st, const RowSubset* sub) {
+                      cudaStream_t st, const RowSubset* sub, const uint8_t* nz) {
   // 256-bit gathers need a 32-byte aligned table (row pitch D*4 is a multiple of 32 for these D);
   // SPEX_SPMM_LDG128=1 forces the 128-bit kernels (A/B measurements)
   static const bool force128 = [] {
@@ -620,17 +720,21 @@ static int launch_vec(const int64_t* rowptr, const int32_t* col, const float* va
   }();
   const bool v8 = !force128 && (reinterpret_cast<uintptr_t>(X) & 31u) == 0;
   const bool hot = plan && (plan->flags & SPEX_PLAN_COL_HOTBIT);
-  if (hot) {
-    if (v8) return launch_vec_h<D, U, true, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
-    return launch_vec_h<D, U, true, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+  if (nz && v8) {   // sparse-input variant (only with the 256-bit kernels; otherwise the mask is simply not used)
+    if (hot) return launch_vec_h<D, U, true, true, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nz);
+    return launch_vec_h<D, U, false, true, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nz);
   }
-  if (v8) return launch_vec_h<D, U, false, true>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
-  return launch_vec_h<D, U, false, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+  if (hot) {
+    if (v8) return launch_vec_h<D, U, true, true, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nullptr);
+    return launch_vec_h<D, U, true, false, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nullptr);
+  }
+  if (v8) return launch_vec_h<D, U, false, true, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nullptr);
+  return launch_vec_h<D, U, false, false, false>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nullptr);
 }
 
 int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, const float* X,
                 int64_t n_rows, int32_t D, const Epilogue& ep, const spex_long_plan* plan,
-                cudaStream_t st, const RowSubset* sub = nullptr) {
+                cudaStream_t st, const RowSubset* sub = nullptr, const uint8_t* nz = nullptr) {
   SPEX_RETURN_IF(!rowptr || !X || n_rows < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(n_rows > 0 && (!col || !val), SPEX_E_BADARG);
   SPEX_RETURN_IF(D <= 0 || (D & 3) || D > 512, SPEX_E_BADDIM);
@@ -645,12 +749,12 @@ int spmm_launch(const int64_t* rowptr, const int32_t* col, const float* val, con
   }
   if (n_rows == 0) return 0;
   switch (D) {
-    case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
-    case 64: return launch_vec<64, SPEX_U64>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
-    case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st, sub);
+    case 32: return launch_vec<32, 4>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nz);
+    case 64: return launch_vec<64, SPEX_U64>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nz);
+    case 128: return launch_vec<128, 8>(rowptr, col, val, X, n_rows, ep, plan, st, sub, nz);
     default: break;
   }
-  SPEX_RETURN_IF(sub != nullptr, SPEX_E_BADDIM);   // row subsets: D in {32, 64, 128} only
+  SPEX_RETURN_IF(sub != nullptr, SPEX_E_BADDIM);   // row subsets: D in {32, 64, 128} only (a mask is just ignored)
   SPEX_RETURN_IF(plan && (plan->flags & SPEX_PLAN_COL_HOTBIT), SPEX_E_BADDIM);  // D in {32,64,128} only
   SPEX_RETURN_IF(ep.partial_in != nullptr || ep.pub_src != nullptr || ep.adam_p != nullptr, SPEX_E_BADDIM);  // same
   // generic path handles long rows serially (no plan needed; still deterministic)
@@ -749,10 +853,10 @@ extern "C" int spex_spmm_csr_f32(const int64_t* rowptr, const int32_t* col, cons
 extern "C" int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                                       const float* X, int64_t n_rows, int32_t D, const int32_t* rows,
                                       int64_t n_sel, const int32_t* long_slots, int32_t n_long_sel,
-                                      const int32_t* seg_ids, int32_t n_seg_sel, float* Y, const float* addend,
-                                      float addend_scale, float* Z, float z_scale, const spex_long_plan* plan,
-                                      void* stream) {
-  SPEX_RETURN_IF(n_sel < 0 || n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows), SPEX_E_BADARG);
+                                      const int32_t* seg_ids, int32_t n_seg_sel, const uint8_t* x_nonzero,
+                                      float* Y, const float* addend, float addend_scale, float* Z, float z_scale,
+                                      const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows), SPEX_E_BADARG);
   SPEX_RETURN_IF(n_long_sel > 0 && (!long_slots || !seg_ids || !plan || n_seg_sel < n_long_sel), SPEX_E_BADARG);
   if (n_sel == 0) return 0;
   Epilogue ep{};
@@ -762,7 +866,8 @@ extern "C" int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col,
   ep.Z = Z;
   ep.z_scale = z_scale;
   RowSubset sub{rows, n_sel, long_slots, n_long_sel, seg_ids, n_seg_sel};
-  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, &sub);
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, n_sel < 0 ? nullptr : &sub,
+                     x_nonzero);
 }
 
 // The row-subset layer with the fused exchange of the row-partitioned modes: the listed rows (LOCAL ids of this
@@ -774,12 +879,11 @@ extern "C" int spex_spmm_csr_rows_f32(const int64_t* rowptr, const int32_t* col,
 extern "C" int spex_spmm_csr_rows_exchange_f32(const int64_t* rowptr, const int32_t* col, const float* val,
                                                const float* X, int64_t n_rows, int32_t D, const int32_t* rows,
                                                int64_t n_sel, const int32_t* long_slots, int32_t n_long_sel,
-                                               const int32_t* seg_ids, int32_t n_seg_sel, int64_t out_row_offset,
-                                               float* mcast_Y, float* const* peer_Y_host, int32_t n_peers,
-                                               const float* addend, float addend_scale, float* Z, float z_scale,
-                                               const spex_long_plan* plan, void* stream) {
-  SPEX_RETURN_IF(n_sel < 0 || n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows) || out_row_offset < 0,
-                 SPEX_E_BADARG);
+                                               const int32_t* seg_ids, int32_t n_seg_sel, const uint8_t* x_nonzero,
+                                               int64_t out_row_offset, float* mcast_Y, float* const* peer_Y_host,
+                                               int32_t n_peers, const float* addend, float addend_scale, float* Z,
+                                               float z_scale, const spex_long_plan* plan, void* stream) {
+  SPEX_RETURN_IF(n_long_sel < 0 || n_seg_sel < 0 || (n_sel > 0 && !rows) || out_row_offset < 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(n_long_sel > 0 && (!long_slots || !seg_ids || !plan || n_seg_sel < n_long_sel), SPEX_E_BADARG);
   SPEX_RETURN_IF(mcast_Y && n_peers > 0, SPEX_E_BADARG);
   SPEX_RETURN_IF(n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_Y_host), SPEX_E_BADARG);
@@ -798,7 +902,8 @@ extern "C" int spex_spmm_csr_rows_exchange_f32(const int64_t* rowptr, const int3
     ep.peer[p] = peer_Y_host[p];
   }
   RowSubset sub{rows, n_sel, long_slots, n_long_sel, seg_ids, n_seg_sel};
-  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, &sub);
+  return spmm_launch(rowptr, col, val, X, n_rows, D, ep, plan, (cudaStream_t)stream, n_sel < 0 ? nullptr : &sub,
+                     x_nonzero);
 }
 
 extern "C" int spex_spmm_csr_f32_push(const int64_t* rowptr, const int32_t* col, const float* val,

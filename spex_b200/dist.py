@@ -196,17 +196,20 @@ class PartitionedPropagator:
             dist.all_reduce(self._flag, group=self.group)
 
     # ---- one layer --------------------------------------------------------------------------------
-    def _layer(self, X_full, Y_local, addend, Z_local, z_scale, push_buf=None, publish=None, subset=None):
-        if subset is not None:
-            # restricted to a row list (receptive field of a mini-batch), same fused exchange
+    def _layer(self, X_full, Y_local, addend, Z_local, z_scale, push_buf=None, publish=None, subset=None,
+               x_nonzero=None):
+        if subset is not None or x_nonzero is not None:
+            # restricted to a row list (receptive field of a mini-batch) and / or reading a table that is zero
+            # outside the rows x_nonzero marks; same fused exchange
             from ._capi import call, ptr, stream_ptr
 
-            rows, slots, segs = subset
+            rows, slots, segs = subset if subset is not None else (None, None, None)
             mc = C.c_void_p(self._mc[push_buf]) if (push_buf is not None and self.mode == "mcast") else None
             peers = self._peer_ptrs[push_buf] if (push_buf is not None and self.mode == "push") else None
             call("spex_spmm_csr_rows_exchange_f32", ptr(self.g.rowptr), ptr(self.g.col), ptr(self.g.val), ptr(X_full),
-                 self.g.n_rows, self.D, ptr(rows), rows.numel(), ptr(slots), 0 if slots is None else slots.numel(),
-                 ptr(segs), 0 if segs is None else segs.numel(), self.r0, mc, peers,
+                 self.g.n_rows, self.D, ptr(rows), -1 if rows is None else rows.numel(), ptr(slots),
+                 0 if slots is None else slots.numel(), ptr(segs), 0 if segs is None else segs.numel(),
+                 ptr(x_nonzero), self.r0, mc, peers,
                  self.world if peers is not None else 0, ptr(addend), 1.0, ptr(Z_local), float(z_scale),
                  self.g.plan(self.D), stream_ptr())
             return
@@ -382,7 +385,7 @@ class PartitionedPropagator:
 
     def propagate(self, E0_local: torch.Tensor, out: torch.Tensor = None,
                   next_E0_local: torch.Tensor = None, next_ready=None, first_full: torch.Tensor = None,
-                  adam: dict = None, row_sets=None) -> torch.Tensor:
+                  adam: dict = None, row_sets=None, x_masks=None) -> torch.Tensor:
         """E0_local: this rank's rows [r0, r1) of the fused table.  Returns mean_k E^(k)[r0:r1]
         (written into `out` if given).  `next_E0_local`: this rank's rows of the table of the NEXT
         call, if the caller already has it (an inference / evaluation sweep over many tables, or
@@ -395,7 +398,9 @@ class PartitionedPropagator:
         as the gradient of `p` by a dense Adam fused into the last layer's epilogue, and the updated rows of
         `p` are published as the next call's table (spex_spmm_csr_f32_adam).
         `row_sets` (fused modes; from receptive_sets(S)): layer k computes - and exchanges - only the rows
-        row_sets[k] (None = all); only the rows S = row_sets[K] of the result are then valid."""
+        row_sets[k] (None = all); only the rows S = row_sets[K] of the result are then valid.
+        `x_masks` (fused modes): x_masks[k] = uint8 [N] marking the rows of layer k's INPUT table that may be
+        non-zero (None = dense): gathers of the other rows are skipped (bit-identical, see spmm_rows)."""
         K = self.K
         if out is None:
             out = torch.empty_like(E0_local)
@@ -452,8 +457,12 @@ class PartitionedPropagator:
                     if publish is not None:
                         raise ValueError("row_sets cannot be combined with a published next table")
                     subset = self.g.row_subset(self._own(row_sets[k + 1]))
+                xm = x_masks[k + 1] if x_masks is not None else None
+                if xm is not None and publish is not None:
+                    raise ValueError("x_masks cannot be combined with a published next table")
                 self._layer(X_full, None, addend, out, inv if last else 1.0,
-                            push_buf=None if last else (a + k + 1) % nt, publish=publish, subset=subset)
+                            push_buf=None if last else (a + k + 1) % nt, publish=publish, subset=subset,
+                            x_nonzero=xm)
                 if publish is not None:
                     done = torch.cuda.Event()
                     done.record()
@@ -637,13 +646,24 @@ class PartitionedTrainer:
         # backward mirror of the receptive field: H_j = g + A^T H_{j-1} is non-zero only on sets[K - j], so layer j
         # (j < K) computes and exchanges those rows into a zeroed table (zeroed here, before the all-reduce that
         # orders it ahead of every peer's stores)
-        bsets = None
+        bsets = bmasks = None
         if sets is not None and self.fused and self.receptive_backward:
+            from . import ops
+
             bsets = [None] * (p.K + 1)
-            for j in range(1, p.K):
+            bmasks = [None] * (p.K + 1)
+            x_rows = sets[p.K]                       # layer 1 reads the gradient table: non-zero on the batch rows
+            for j in range(1, p.K):                  # (the last layer is the fused Adam kernel: dense)
+                if x_rows is not None:
+                    d = p._sum_over_ranks(p.g.degree_sum(p._own(x_rows)))
+                    if d <= ops.SPARSE_INPUT_MAX_EDGE_FRAC * p._nnz_global:
+                        bmasks[j] = ops.nonzero_mask(p.N, x_rows)
                 if sets[p.K - j] is not None:
                     bsets[j] = sets[p.K - j]
                     p.zero_slot(j)
+                    x_rows = sets[p.K - j]           # the next layer reads a zeroed table holding these rows
+                else:
+                    x_rows = None
         if p.world > 1:
             dist.all_reduce(R, group=p.group)
         Ru, Ri = R[:B], R[B:]
@@ -662,7 +682,7 @@ class PartitionedTrainer:
             self._dirty = rows
             if bsets is not None and any(b is not None for b in bsets):
                 self.dW.zero_()     # a restricted first layer writes g + A g on its rows only; the rest is 0
-            p.propagate(self.G_full[r0:r1], out=self.dW, first_full=self.G_full, row_sets=bsets,
+            p.propagate(self.G_full[r0:r1], out=self.dW, first_full=self.G_full, row_sets=bsets, x_masks=bmasks,
                         adam={"p": self.W, "m": self.m, "v": self.v, "lr": self.lr, "beta1": self.betas[0],
                               "beta2": self.betas[1], "eps": self.eps, "step": self.t})
             return loss

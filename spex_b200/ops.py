@@ -476,11 +476,21 @@ def spmm(g: DeviceGraph, X: torch.Tensor, Y: Optional[torch.Tensor] = None,
     return Y if Y is not None else Z
 
 
+def nonzero_mask(n: int, rows: torch.Tensor) -> torch.Tensor:
+    """uint8 [n], 1 on `rows`: the x_nonzero argument of spmm_rows (rows of X that may be non-zero)."""
+    m = torch.zeros(n, dtype=torch.uint8, device=rows.device)
+    m[rows] = 1
+    return m
+
+
 def spmm_rows(g: DeviceGraph, X: torch.Tensor, subset, Y: Optional[torch.Tensor] = None,
               addend: Optional[torch.Tensor] = None, addend_scale: float = 1.0,
-              Z: Optional[torch.Tensor] = None, z_scale: float = 1.0, val: Optional[torch.Tensor] = None):
-    """spmm() restricted to the rows of `subset` (= g.row_subset(rows)): the listed rows of Y / Z get exactly
-    the values a full layer gives them, the other rows are left untouched."""
+              Z: Optional[torch.Tensor] = None, z_scale: float = 1.0, val: Optional[torch.Tensor] = None,
+              x_nonzero: Optional[torch.Tensor] = None):
+    """spmm() restricted to the rows of `subset` (= g.row_subset(rows); None = all rows): the listed rows of
+    Y / Z get exactly the values a full layer gives them, the other rows are left untouched.  `x_nonzero`
+    (uint8 [n_cols]): X is exactly zero on the rows it marks 0 - those gathers are skipped, the result is
+    bit-identical."""
     _need_cuda(X)
     X = _f32c(X)
     D = X.shape[1]
@@ -488,13 +498,19 @@ def spmm_rows(g: DeviceGraph, X: torch.Tensor, subset, Y: Optional[torch.Tensor]
         raise ValueError(f"X has {X.shape[0]} rows, graph has {g.n_cols} columns")
     if Y is None and Z is None:
         raise ValueError("spmm_rows writes into caller-provided Y and/or Z")
-    rows, slots, segs = subset
+    rows, slots, segs = subset if subset is not None else (None, None, None)
     v = g.val if val is None else val
-    call("spex_spmm_csr_rows_f32", ptr(g.rowptr), ptr(g.col), ptr(v), ptr(X), g.n_rows, D, ptr(rows), rows.numel(),
-         ptr(slots), 0 if slots is None else slots.numel(), ptr(segs), 0 if segs is None else segs.numel(),
-         ptr(Y), ptr(addend), float(addend_scale), ptr(Z), float(z_scale), g.plan(D), stream_ptr())
+    if x_nonzero is not None and (x_nonzero.dtype != torch.uint8 or x_nonzero.numel() != g.n_cols):
+        raise ValueError("x_nonzero must be uint8 [n_cols]")
+    call("spex_spmm_csr_rows_f32", ptr(g.rowptr), ptr(g.col), ptr(v), ptr(X), g.n_rows, D, ptr(rows),
+         -1 if rows is None else rows.numel(), ptr(slots), 0 if slots is None else slots.numel(), ptr(segs),
+         0 if segs is None else segs.numel(), ptr(x_nonzero), ptr(Y), ptr(addend), float(addend_scale), ptr(Z),
+         float(z_scale), g.plan(D), stream_ptr())
 
 
+# A layer's input is treated as sparse (x_nonzero mask, gathers of zero rows skipped) while the rows that may be
+# non-zero hold fewer than this fraction of nnz(A)
+SPARSE_INPUT_MAX_EDGE_FRAC = 0.3
 # A layer is restricted to a row list only while the list's edges stay below SUBSET_MAX_EDGE_FRAC of nnz(A)
 # (beyond it the skipped rows no longer pay for the indirection), and a list is expanded to its neighbour set
 # only while it has fewer than EXPAND_MAX_EDGE_FRAC * nnz(A) edges (the set is built by a gather + sort).
@@ -562,17 +578,26 @@ class _PropagateMeanRows(torch.autograd.Function):
         # H_0 = g; H_j = g + A^T H_{j-1}, non-zero only on R[K - j]: a restricted layer writes its rows into a
         # zero table (zero-filled once; afterwards only the rows of the previous step are cleared)
         X = g
+        x_rows = R[K]              # rows of X that may be non-zero (None: dense)
         for j in range(1, K + 1):
             last = j == K
             sub = subs[K - j] if j < K else None
             kw = dict(addend=g, addend_scale=1.0, z_scale=inv if last else 1.0, val=ctx.valT)
+            mask = None
+            if x_rows is not None and graph.degree_sum(x_rows) <= SPARSE_INPUT_MAX_EDGE_FRAC * graph.nnz:
+                mask = nonzero_mask(N, x_rows)       # most gathers of this layer would fetch zero rows: skip them
             if sub is None:
                 Z = dE0 if last else tmp[(j - 1) & 1]
-                spmm(graph, X, Z=Z, **kw)
+                if mask is None:
+                    spmm(graph, X, Z=Z, **kw)
+                else:
+                    spmm_rows(graph, X, None, Z=Z, x_nonzero=mask, **kw)
+                x_rows = None
             else:
                 Z, zkey = workspaces.get(f"prop_bwd_rows{j}", g.shape, g.device, zero=True)
-                spmm_rows(graph, X, sub, Z=Z, **kw)
+                spmm_rows(graph, X, sub, Z=Z, x_nonzero=mask, **kw)
                 workspaces.mark(zkey, R[K - j])
+                x_rows = R[K - j]
             X = Z
         return dE0, None, None, None, None, None
 

@@ -60,6 +60,39 @@ def test_row_subset_layer_is_bit_identical(cuda_device, blocked, monkeypatch):
         assert torch.equal(Y2[rows], Yf2[rows])
 
 
+@pytest.mark.parametrize("blocked", [False, True])
+@pytest.mark.parametrize("frac", [0.002, 0.08, 0.6])
+def test_sparse_input_mask_is_bit_identical(cuda_device, blocked, frac, monkeypatch):
+    """x_nonzero: a table that is zero outside a marked row set gives the same bits whether the zero rows are
+    gathered (dense layer) or skipped (masked kernels) - all rows and a row subset, D = 64 / 32 / 128, ragged
+    tails, long rows, both long-row plans, from almost empty to mostly full masks."""
+    from spex_b200 import ops
+
+    if blocked:
+        monkeypatch.setattr(ops.DeviceGraph, "L2_WINDOW_BYTES", 64 * 1024)
+        monkeypatch.setattr(ops.DeviceGraph, "MIN_CB_COLS", 64)
+        monkeypatch.setattr(ops.DeviceGraph, "HUB_EDGES_PER_BLOCK", 4)
+    g, nur, m = _graph(cuda_device, seg_len=32)
+    N = nur + m
+    gen = torch.Generator().manual_seed(int(frac * 1000))
+    nzrows = torch.randperm(N, generator=gen)[: max(int(N * frac), 3)].to(cuda_device)
+    mask = ops.nonzero_mask(N, nzrows)
+    for D in (64, 32, 128):
+        torch.manual_seed(D)
+        X = torch.zeros(N, D, device=cuda_device)
+        X[nzrows] = torch.randn(nzrows.numel(), D, device=cuda_device)
+        add = torch.randn(N, D, device=cuda_device)
+        Zd = torch.empty_like(X)
+        ops.spmm(g, X, addend=add, Z=Zd, z_scale=0.5)
+        Zm = torch.empty_like(X)
+        ops.spmm_rows(g, X, None, addend=add, Z=Zm, z_scale=0.5, x_nonzero=mask)
+        assert torch.equal(Zm, Zd)
+        rows = torch.unique(torch.cat([torch.randperm(N, generator=gen)[:2000], g.long_rows[:3].long().cpu()])).to(cuda_device)
+        Zs = torch.full_like(X, 3.0)
+        ops.spmm_rows(g, X, g.row_subset(rows), addend=add, Z=Zs, z_scale=0.5, x_nonzero=mask)
+        assert torch.equal(Zs[rows], Zd[rows])
+
+
 @pytest.mark.parametrize("K", [1, 2, 3])
 @pytest.mark.parametrize("expand_all", [False, True])
 def test_propagate_mean_rows_bit_identical(cuda_device, K, expand_all, monkeypatch):
