@@ -564,8 +564,8 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
             "steps_per_s": 1e3 / ms_step, "batch": B, "loss": loss_val, "phases_ms": {k: round(v, 3) for k, v in phases.items()},
             "receptive_field": {"rows_per_layer": rf_rows, "edges_per_layer": rf_edges, "nnz": g.nnz,
                                 "note": "layers 1..K of the forward restricted to the rows the batch depends on (null = "
-                                        "all rows); the backward mirrors it; loss and gradients bit-identical to the "
-                                        "full step"},
+                                        "all rows); the backward mirrors it and skips the gathers of rows known to be "
+                                        "zero (x_nonzero masks); loss and gradients bit-identical to the full step"},
             "full_computer_step": {"value": ms_full, "unit": "ms", "loss": loss_full,
                                    "phases_ms": {k: round(v, 3) for k, v in phases_full.items()},
                                    "note": "the reference's literal step: computer() over all N rows in forward and "
