@@ -487,6 +487,11 @@ spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
   // two-pass rows: pass 1 = hot edges [start, rowmid), pass 2 = cold edges [rowmid, end)
   if (pass == 1) end = rowmid[row];
   if (pass == 2) start = rowmid[row];
+  // sparse-input layers are bound by the per-row latency chain (rowptr -> col/val -> mask -> gathers -> addend):
+  // ask L2 for the epilogue's addend row now (in the dense layers, which are throughput-bound, the same prefetch
+  // measured no gain: profiles/r02_spmm_ldg256.md)
+  if (kMask && ep.addend && lane < RowShape<D>::LPR && (lane & 7) == 0)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.addend + row * D + lane * 4));
   const float4 acc = row_sum<D, U, kHot, kV8, kMask>(col, val, X, start, end, lane, nz);
   row_epilogue<D>(ep, acc, row, lane);
 }
