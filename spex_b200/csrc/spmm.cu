@@ -4,19 +4,28 @@
 // and, through the fused epilogue, stack+mean       model.py:94-95
 // and the autograd of both                          main_rec.py:35
 //
-// Design (HBM-bandwidth kernel, 0.48 flop/B — no tensor cores on purpose):
-//   * one warp owns one output row; the row's (col,val) run is read coalesced, 32 edges at a
-//     time, with streaming cache hints (read-once), and broadcast by warp shuffles;
-//   * a 256-byte embedding row (D=64 fp32) is fetched by 16 lanes x 128-bit, so one LDG.128
-//     warp instruction gathers G=2 neighbour rows; U of those are issued back to back before the
-//     first FMA (U*G rows = U*512 B in flight per warp);
-//   * lane groups accumulate disjoint edge subsets in edge order and are combined by a fixed
-//     xor-shuffle tree: the summation order is a pure function of the row => bit-reproducible,
-//     no atomics;
-//   * rows longer than plan->seg_len are skipped here and reduced by two extra launches
-//     (warp per segment -> partial rows -> warp per long row), again in a fixed order;
-//   * epilogue: Y = acc (next layer's input) and/or Z = (addend*a + acc)*b (running layer mean
-//     forward, g + A^T G backward).  The last layer writes only Z.
+// Design (0.48 flop/B: an HBM / L2-slice bandwidth kernel - no tensor cores on purpose):
+//   * one warp owns one output row, one warp per CTA (the block scheduler backfills a warp slot as soon as a
+//     row is done); the row's (col,val) run is read coalesced, 32 edges at a time, with streaming hints, one
+//     batch ahead of the gathers;
+//   * shipped gather loop (warp_row_accumulate8, 32-byte aligned tables): LDG.256 - 8 lanes x 32 B cover a
+//     256-byte row (D=64), one warp instruction fetches 4 neighbour rows, 4 in flight per lane before the first
+//     FMA; the batch's edges are dealt to the lane groups in consecutive runs so that a segmented shuffle with
+//     an immediate lane delivers them; hot columns (bit 31 of col) load with L2::evict_last, the rest with
+//     evict_first (static qualifiers, 256-bit loads only).  4.2 instructions per edge.
+//     Fallback for 16-byte aligned tables / SPEX_SPMM_LDG128=1: the 128-bit loop of round 1
+//     (warp_row_accumulate: 16 lanes per row, policy descriptors);
+//   * lane groups accumulate disjoint edge runs in edge order and are combined by a fixed xor-shuffle tree: the
+//     summation order is a pure function of the row => bit-reproducible, no atomics;
+//   * rows longer than plan->seg_len are skipped here and reduced by two extra launches (warp per segment ->
+//     partial rows -> warp per long row), hub rows cut at column-block boundaries and listed block-major so
+//     that the table window they gather from stays in L2;
+//   * epilogue: Y = acc (next layer's input) and/or Z = (addend*a + acc)*b (running layer mean forward,
+//     g + A^T G backward), optionally stored into every peer's table (P2P or one NVLS multicast store), with the
+//     next call's table or a dense Adam step riding on the last layer (row-partitioned modes);
+//   * a layer can be restricted to a ROW LIST (RowSubset: the receptive field of a mini-batch) and can be told
+//     which rows of X may be non-zero (x_nonzero: the sparse gradient tables of the training backward); both
+//     keep every computed row bit-identical to the full dense layer.
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
