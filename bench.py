@@ -74,6 +74,34 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def profile_metric(names, key):
+    """Sum of metric `key` (a byte count) over the kernels named in `names`, from the newest committed ncu
+    summary that lists them all with that metric; None if there is none."""
+    import glob
+
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.json")), reverse=True):
+        try:
+            rows = json.load(open(path))
+        except Exception:
+            continue
+        tot, seen = 0.0, set()
+        for r in rows:
+            kn = r.get("Kernel Name", "")
+            hit = next((n for n in names if n in kn), None)
+            if hit is None or hit in seen or key not in r:
+                continue
+            try:
+                v, u = r[key].split()
+                tot += float(v) * unit[u]
+            except Exception:
+                break
+            seen.add(hit)
+        if len(seen) == len(names):
+            return tot
+    return None
+
+
 def profile_traffic(names):
     """DRAM bytes (read + write) of the kernels whose name contains one of `names`, summed, from the newest
     ncu summary under profiles/ that lists them all (profiles/ncu_summary.py output); (None, None) if there is
@@ -802,7 +830,10 @@ def run_ours(args):
     # DRAM traffic per layer: NOT measured by this run - read from the newest committed `ncu --set full` summary
     # of this exact workload (full scale, one GPU) under profiles/, and labelled with its file name
     traffic, traffic_src = (None, None)
+    l2_bytes = None
     if world == 1 and args.scale == 1.0:
+        l2_bytes = profile_metric(["spmm_rows_kernel<64", "spmm_seg_list_kernel<64", "spmm_long_fix_list_kernel<64"],
+                                  "l1tex__m_xbar2l1tex_read_bytes.sum")
         traffic, traffic_src = profile_traffic(["spmm_rows_kernel<64", "spmm_seg_list_kernel<64", "spmm_long_fix_list_kernel<64"])
     roofline = {"bound": "hbm", "kernel": "spmm_rows_kernel<64,8,1,1> + spmm_seg_list_kernel<64,8,1,1> + "
                                           "spmm_long_fix_list_kernel<64,8> (one layer = one launch of each)",
@@ -813,6 +844,12 @@ def run_ours(args):
                 # the gathers.  The DRAM-side view of the same launch: measured traffic / time / peak.
                 "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,
                 "dram_frac": (traffic / t_launch / 1e9 / hbm_peak) if traffic else None,
+                # what actually bounds the layer: bytes the L2 slices deliver to the SMs
+                # (ncu l1tex__m_xbar2l1tex_read_bytes, same committed capture), against the ~6300 B/clk LTS cap
+                # that B300_MICROARCH.md measures (no B200 figure in MEASURED_PEAKS.json: reported, not a frac)
+                "l2_to_sm_bytes": l2_bytes,
+                "l2_to_sm_achieved": (l2_bytes / t_launch / 1e9) if l2_bytes else None,
+                "l2_to_sm_cap_note": "~6300 B/clk full chip = 10.7 TB/s at 1.7 GHz, 12.4 TB/s at 1.965 GHz (guide, B300)",
                 "note": "per-launch time = step time / K (exchange included at N>1); traffic from ncu, "
                         "per layer"}
 

@@ -14,6 +14,7 @@ from collections import defaultdict
 
 KEEP = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
