@@ -523,13 +523,15 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
     # both arms start from the same weights and moments, so their first timed losses are comparable
     W0 = W.detach().clone()
     ms_full, phases_full, loss_full = measure(False)
+    W_full = W.detach().clone()          # weights after the 7 literal steps
     with torch.no_grad():
         W.copy_(W0)
         mom.zero_()
         var.zero_()
     step_no[0] = 0
     ms_step, phases, loss_val = measure(True)
-    del W0
+    same_weights = bool(torch.equal(W.detach(), W_full))   # the same 7 steps on the receptive-field path: same bits
+    del W0, W_full
     S_rows = torch.unique(torch.cat([users, items + nur]))
     R = ops.receptive_rows(g, S_rows, K_LAYERS)
     rf_rows = [None if r is None else int(r.numel()) for r in R[1:]]
@@ -597,7 +599,8 @@ def bench_train_step(args, torch, ops, _capi, g, table, nur, m, N, hbm_peak, pea
             "full_computer_step": {"value": ms_full, "unit": "ms", "loss": loss_full,
                                    "phases_ms": {k: round(v, 3) for k, v in phases_full.items()},
                                    "note": "the reference's literal step: computer() over all N rows in forward and "
-                                           "backward (main_rec.py:34-35)", "same_loss_as_receptive_path": loss_full == loss_val},
+                                           "backward (main_rec.py:34-35)", "same_loss_as_receptive_path": loss_full == loss_val,
+                                   "same_weights_after_7_steps_as_receptive_path": same_weights},
             "config": {"workload": f"main_rec.py:30-37 step on the bench graph: forward(K={K_LAYERS}) + BCE (1 positive + 5 "
                                    f"negatives per user, device sampler) + backward + dense Adam over {N} x {D}",
                        "edges_per_step": 2 * K_LAYERS * g.nnz},
@@ -1098,10 +1101,13 @@ def run_ours(args):
             barrier()
             t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()) / n_tr, float(tloss.item())
+            return float(t.item()) / n_tr, float(tloss.item()), tr.W.detach().clone()
 
-        ms_tr_full, loss_full = measure_tr(False)
-        ms_tr, loss_rf = measure_tr(True)
+        ms_tr_full, loss_full, W_a = measure_tr(False)
+        ms_tr, loss_rf, W_b = measure_tr(True)
+        same_w = torch.tensor([1.0 if torch.equal(W_a, W_b) else 0.0], device=dev)
+        dist.all_reduce(same_w, op=dist.ReduceOp.MIN)     # every rank's slice of the weights after the 6 steps
+        del W_a, W_b
         sets = prop.receptive_sets(torch.unique(torch.cat([tu, ti + nur])))
         trainj = {"metric": "lightgcn_train_step_ms", "value": ms_tr, "unit": "ms", "higher_is_better": False,
                   "steps_per_s": 1e3 / ms_tr, "batch": Bt, "loss": loss_rf,
@@ -1111,7 +1117,8 @@ def run_ours(args):
                                               "backward mirrors it (first layer restricted, written into zeroed "
                                               "tables); loss and weights bit-identical to the full step"},
                   "full_computer_step": {"value": ms_tr_full, "unit": "ms", "loss": loss_full,
-                                         "same_loss_as_receptive_path": loss_full == loss_rf},
+                                         "same_loss_as_receptive_path": loss_full == loss_rf,
+                                         "same_weights_after_6_steps_as_receptive_path": bool(same_w.item() > 0)},
                   # edges actually traversed per second: quoted on the FULL step
                   "gedges_per_s_fwd_plus_bwd": 2 * K_LAYERS * nnz / (ms_tr_full * 1e-3) / 1e9,
                   "config": {"workload": f"main_rec.py:30-37 step, row-partitioned x{world}: forward + BCE (1 positive + 5 "
