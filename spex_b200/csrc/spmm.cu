@@ -260,6 +260,9 @@ __device__ __forceinline__ float4 warp_row_accumulate8(const int32_t* __restrict
 #ifndef SPEX_V8_U
 #define SPEX_V8_U 4
 #endif
+#ifndef SPEX_MASK_U
+#define SPEX_MASK_U 2
+#endif
 #ifndef SPEX_V8_MINB
 #define SPEX_V8_MINB 32
 #endif
@@ -278,7 +281,10 @@ __device__ __forceinline__ float4 warp_row_accumulate8_masked(const int32_t* __r
                                                               const uint8_t* __restrict__ nz, int64_t start,
                                                               int64_t end, int lane) {
   constexpr int LPR8 = D / 8;
-  constexpr int U = D >= 64 ? 4 : 2;
+  // active edges taken per lane group and loop trip: with ~8 % of the edges active a group of 8 holds 0-2 of
+  // them, and every slot of a trip costs its shuffles and predicates whether it is used or not (ncu: U = 4 left
+  // the kernel instruction-bound at 7.4 warp instructions per edge)
+  constexpr int U = SPEX_MASK_U;
   const int grp = lane / LPR8, sub = lane % LPR8;
   const float* Xs = X + sub * 8;
   f8 acc;
