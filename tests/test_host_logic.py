@@ -156,6 +156,39 @@ def test_capi_exports_every_declared_symbol():
     assert "SPEX_E_ALIGN" in _capi.error_string(-3)
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding in _capi.SIGNATURES passes exactly the parameters include/spex_b200.h declares, with the
+    same kind (pointer / 32-bit int / 64-bit int / float) in the same position: a drift between the two is
+    undefined behaviour at the first call, not an import error."""
+    from spex_b200 import _capi
+
+    hdr = open(os.path.join(ROOT, "include", "spex_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|int64_t|const char\s*\*)\s+(spex_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(_capi.SIGNATURES)
+
+    def kind_c(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return "p"
+        base = param.rsplit(" ", 1)[0] if " " in param else param
+        return {"int32_t": "i32", "int": "i32", "uint32_t": "i32", "int64_t": "i64", "uint64_t": "i64",
+                "float": "f"}[base.replace("const ", "").strip()]
+
+    def kind_py(t):
+        if t in (ctypes.c_int32, ctypes.c_int, ctypes.c_uint32):
+            return "i32"
+        if t in (ctypes.c_int64, ctypes.c_uint64):
+            return "i64"
+        if t is ctypes.c_float:
+            return "f"
+        return "p"      # c_void_p, c_char_p, POINTER(...)
+
+    for name, (_res, argtypes) in _capi.SIGNATURES.items():
+        params = [p for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        assert [kind_c(p) for p in params] == [kind_py(t) for t in argtypes], name
+
+
 def test_product_path_refuses_cpu():
     from helpers import make_args
     from spex_b200.dataloader import SyntheticDataset
