@@ -1143,7 +1143,11 @@ def run_ours(args):
         ge, dt = cpu_time_computer(A, snu, sm_, 3, 1)
         cpu = {"value": ge, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle computer() (torch.sparse.mm, the reference's CPU backend) K={K_LAYERS} D={D} "
-                         f"on {snu} users x {sm_} items, nnz(A)={A._nnz()}, 3 timed runs, {dt * 1e3:.0f} ms each"}
+                         f"on {snu} users x {sm_} items, nnz(A)={A._nnz()}, 3 timed runs, {dt * 1e3:.0f} ms each",
+               "larger_sample_on_record": "1/10 scale (1 M x 500 k, nnz 2e8), same box type: 0.0111 GEdges/s, 54 s per "
+                                          "K=3 step (profiles/r02_reference_arm_scale_0.1.json; --cpu-sample-scale 0.1): "
+                                          "the CPU path gets slower per edge as the table outgrows its caches, so "
+                                          "the 1/100 sample flatters it"}
 
     if rank == 0:
         line = {
